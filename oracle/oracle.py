@@ -1,0 +1,224 @@
+"""TEST INFRASTRUCTURE — ctypes front-end of the C oracle (oracle/mapf_oracle.c).
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs
+may import this module.  The product package `mapf_rl_b200` never does.
+
+`OracleEnv` mirrors the reference `Environment` surface used on the hot path
+(environment.py:198-215 load, :278-430 step, :433-467 observe, :217-276 get_navi_map) so parity
+tests read like the reference's callers.  `OracleSumTree` mirrors buffer.py:16-105.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+import threading
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "libmapf_oracle.so")
+_lib = None
+
+# config.py:8-12, in the repo-wide order move, stay_on_goal, stay_off_goal, collision, finish
+REWARD_FN = dict(move=-0.075, stay_on_goal=0, stay_off_goal=-0.075, collision=-0.5, finish=3)
+REWARD_ORDER = ("move", "stay_on_goal", "stay_off_goal", "collision", "finish")
+
+
+def build(force: bool = False) -> str:
+    src = os.path.join(_HERE, "mapf_oracle.c")
+    if force or not os.path.exists(_LIB_PATH) or os.path.getmtime(_LIB_PATH) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-s", "-C", _HERE, "-B"])
+    return _LIB_PATH
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        L = C.CDLL(_LIB_PATH)
+        u8p, i32p, i64p = C.POINTER(C.c_uint8), C.POINTER(C.c_int32), C.POINTER(C.c_int64)
+        f32p, f64p = C.POINTER(C.c_float), C.POINTER(C.c_double)
+        L.mo_step.restype = C.c_int
+        L.mo_step.argtypes = [C.c_int, C.c_int, u8p, i32p, i32p, u8p, f64p, f64p]
+        L.mo_navi.restype = None
+        L.mo_navi.argtypes = [C.c_int, C.c_int, u8p, i32p, i32p, u8p]
+        L.mo_observe.restype = None
+        L.mo_observe.argtypes = [C.c_int, C.c_int, C.c_int, u8p, i32p, u8p, u8p]
+        L.mo_rollout.restype = C.c_long
+        L.mo_rollout.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, u8p, i32p, i32p, u8p, u8p, f64p,
+                                 f32p, u8p, u8p]
+        L.mo_tree_batch_update.restype = None
+        L.mo_tree_batch_update.argtypes = [f64p, C.c_int64, C.c_int, i64p, f64p, C.c_int64]
+        L.mo_tree_batch_sample.restype = None
+        L.mo_tree_batch_sample.argtypes = [f64p, C.c_int64, C.c_int, f64p, C.c_int64, i64p, f64p]
+        L.mo_actor_td.restype = None
+        L.mo_actor_td.argtypes = [C.c_int, C.c_int, f64p, f32p, u8p, f64p]
+        L.mo_learner_td.restype = None
+        L.mo_learner_td.argtypes = [C.c_int64, f32p, f32p, i64p, f32p, f32p, f32p, f32p, f32p]
+        _lib = L
+    return _lib
+
+
+def _p(a: np.ndarray, ct):
+    return a.ctypes.data_as(C.POINTER(ct))
+
+
+def reward_vector(reward_fn=None) -> np.ndarray:
+    rf = REWARD_FN if reward_fn is None else reward_fn
+    return np.asarray([rf[k] for k in REWARD_ORDER], dtype=np.float64)
+
+
+def navi(map_: np.ndarray, goals: np.ndarray):
+    """-> (dist int32[N,L,L], navi uint8[N,4,L,L] unpadded).  environment.py:217-274."""
+    m = np.ascontiguousarray(np.asarray(map_) != 0, dtype=np.uint8)
+    L = m.shape[0]
+    g = np.ascontiguousarray(goals, dtype=np.int32)
+    N = g.shape[0]
+    dist = np.empty((N, L, L), dtype=np.int32)
+    nv = np.empty((N, 4, L, L), dtype=np.uint8)
+    lib().mo_navi(L, N, _p(m, C.c_uint8), _p(g, C.c_int32), _p(dist, C.c_int32), _p(nv, C.c_uint8))
+    return dist, nv
+
+
+class OracleEnv:
+    """Single environment with the reference's load/step/observe contract."""
+
+    def __init__(self, obs_radius: int = 4, reward_fn=None):
+        self.obs_radius = obs_radius
+        self.reward_fn = dict(REWARD_FN if reward_fn is None else reward_fn)
+        self._rf = reward_vector(self.reward_fn)
+
+    def load(self, map_, agents_pos, goals_pos):  # environment.py:198-215
+        self.map = np.ascontiguousarray(np.asarray(map_) != 0, dtype=np.uint8)
+        self.agents_pos = np.ascontiguousarray(agents_pos, dtype=np.int32).copy()
+        self.goals_pos = np.ascontiguousarray(goals_pos, dtype=np.int32).copy()
+        self.num_agents = self.agents_pos.shape[0]
+        self.map_size = (self.map.shape[0], self.map.shape[1])
+        self.steps = 0
+        self.dist_map, self.navi_map = navi(self.map, self.goals_pos)
+
+    def step(self, actions):  # environment.py:278-430
+        a = np.asarray(actions)
+        assert a.shape[0] == self.num_agents, "actions number"
+        assert np.all((a >= 0) & (a < 5)), "action index out of range"
+        a8 = np.ascontiguousarray(a, dtype=np.uint8)
+        rew = np.empty(self.num_agents, dtype=np.float64)
+        pos = self.agents_pos.copy()
+        d = lib().mo_step(self.map_size[0], self.num_agents, _p(self.map, C.c_uint8), _p(pos, C.c_int32),
+                          _p(self.goals_pos, C.c_int32), _p(a8, C.c_uint8), _p(self._rf, C.c_double),
+                          _p(rew, C.c_double))
+        if d == -2:
+            raise RuntimeError("unique")
+        assert d >= 0
+        self.agents_pos = pos
+        self.steps += 1
+        return self.observe(), rew.tolist(), bool(d), {"step": self.steps - 1}
+
+    def observe(self):  # environment.py:433-467
+        F = 2 * self.obs_radius + 1
+        obs = np.empty((self.num_agents, 6, F, F), dtype=np.uint8)
+        lib().mo_observe(self.map_size[0], self.num_agents, self.obs_radius, _p(self.map, C.c_uint8),
+                         _p(self.agents_pos, C.c_int32), _p(self.navi_map, C.c_uint8), _p(obs, C.c_uint8))
+        return obs.astype(bool), self.agents_pos.astype(np.int64)
+
+
+def rollout(maps, pos, goals, navi_maps, actions, reward_fn=None, obs_radius=4, threads=1,
+            want_rewards=True):
+    """Lockstep batch: maps u8[B,L,L], pos/goals i32[B,N,2] (pos updated in place), navi u8[B,N,4,L,L],
+    actions u8[T,B,N].  Returns (rewards f32[T,B,N] | None, done u8[T,B], obs u8[B,N,6,F,F] of last step).
+    `threads` python threads each run a contiguous slice of envs (ctypes releases the GIL)."""
+    B, L = maps.shape[0], maps.shape[1]
+    N = pos.shape[1]
+    T = actions.shape[0]
+    F = 2 * obs_radius + 1
+    rf = reward_vector(reward_fn)
+    rewards = np.zeros((T, B, N), dtype=np.float32) if want_rewards else None
+    done = np.zeros((T, B), dtype=np.uint8)
+    obs = np.zeros((B, N, 6, F, F), dtype=np.uint8)
+    assert maps.dtype == np.uint8 and pos.dtype == np.int32 and goals.dtype == np.int32
+    assert navi_maps.dtype == np.uint8 and actions.dtype == np.uint8
+    for a in (maps, pos, goals, navi_maps, actions):
+        assert a.flags.c_contiguous
+
+    def run(lo, hi):
+        nb = hi - lo
+        if nb <= 0:
+            return
+        # per-slice contiguous views: actions/rewards/done are [T,B,...] so slice-copy them
+        act = np.ascontiguousarray(actions[:, lo:hi])
+        rw = np.zeros((T, nb, N), dtype=np.float32) if want_rewards else None
+        dn = np.zeros((T, nb), dtype=np.uint8)
+        lib().mo_rollout(nb, L, N, obs_radius, T, _p(maps[lo:hi], C.c_uint8), _p(pos[lo:hi], C.c_int32),
+                         _p(goals[lo:hi], C.c_int32), _p(navi_maps[lo:hi], C.c_uint8), _p(act, C.c_uint8),
+                         _p(rf, C.c_double), _p(rw, C.c_float) if want_rewards else None, _p(dn, C.c_uint8),
+                         _p(obs[lo:hi], C.c_uint8))
+        if want_rewards:
+            rewards[:, lo:hi] = rw
+        done[:, lo:hi] = dn
+
+    lib()
+    if threads <= 1:
+        run(0, B)
+    else:
+        bounds = np.linspace(0, B, threads + 1).astype(int)
+        ts = [threading.Thread(target=run, args=(int(bounds[k]), int(bounds[k + 1]))) for k in range(threads)]
+        for t in ts:
+            t.start()
+        for t in ts:
+            t.join()
+    return rewards, done, obs
+
+
+class OracleSumTree:
+    """buffer.py:16-105 with caller-supplied uniforms for batch_sample."""
+
+    def __init__(self, capacity: int):
+        layer = 1
+        while 2 ** (layer - 1) < capacity:
+            layer += 1
+        assert 2 ** (layer - 1) == capacity, "buffer size only support power of 2 size"
+        self.layer = layer
+        self.capacity = capacity
+        self.tree = np.zeros(2 ** layer - 1, dtype=np.float64)
+
+    def batch_sample(self, batch_size: int, uniforms: np.ndarray):
+        u = np.ascontiguousarray(uniforms, dtype=np.float64)
+        idx = np.empty(batch_size, dtype=np.int64)
+        pr = np.empty(batch_size, dtype=np.float64)
+        lib().mo_tree_batch_sample(_p(self.tree, C.c_double), self.capacity, self.layer, _p(u, C.c_double),
+                                   batch_size, _p(idx, C.c_int64), _p(pr, C.c_double))
+        return idx, pr
+
+    def batch_update(self, idxes: np.ndarray, priorities: np.ndarray):
+        assert idxes.dtype == np.int64 and idxes.flags.c_contiguous
+        p = np.ascontiguousarray(priorities, dtype=np.float64)
+        lib().mo_tree_batch_update(_p(self.tree, C.c_double), self.capacity, self.layer, _p(idxes, C.c_int64),
+                                   _p(p, C.c_double), idxes.shape[0])
+
+
+def actor_td(rew_fp16: np.ndarray, q: np.ndarray, act: np.ndarray, capacity: int = 256) -> np.ndarray:
+    """buffer.py:170-177.  rew_fp16: float16[size]; q: float32[size(+1),5]; act: uint8[size]."""
+    size = rew_fp16.shape[0]
+    r = np.asarray(rew_fp16, dtype=np.float16).astype(np.float64)
+    qq = np.ascontiguousarray(q[:size], dtype=np.float32)
+    a = np.ascontiguousarray(act, dtype=np.uint8)
+    td = np.empty(capacity, dtype=np.float64)
+    lib().mo_actor_td(size, capacity, _p(r, C.c_double), _p(qq, C.c_float), _p(a, C.c_uint8), _p(td, C.c_double))
+    return td
+
+
+def learner_td(q_online, q_target_next, action, reward, done, steps):
+    """worker.py:300-308 in fp32 -> (td f32[n], priority f32[n])."""
+    n = q_online.shape[0]
+    qo = np.ascontiguousarray(q_online, dtype=np.float32)
+    qt = np.ascontiguousarray(q_target_next, dtype=np.float32)
+    a = np.ascontiguousarray(action, dtype=np.int64).reshape(-1)
+    r = np.ascontiguousarray(reward, dtype=np.float32).reshape(-1)
+    d = np.ascontiguousarray(done, dtype=np.float32).reshape(-1)
+    s = np.ascontiguousarray(steps, dtype=np.float32).reshape(-1)
+    td = np.empty(n, dtype=np.float32)
+    pr = np.empty(n, dtype=np.float32)
+    lib().mo_learner_td(n, _p(qo, C.c_float), _p(qt, C.c_float), _p(a, C.c_int64), _p(r, C.c_float),
+                        _p(d, C.c_float), _p(s, C.c_float), _p(td, C.c_float), _p(pr, C.c_float))
+    return td, pr
