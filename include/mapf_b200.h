@@ -1,0 +1,177 @@
+/*
+ * mapf_b200.h — C ABI of libmapf_b200.so: the B200-native (sm_100a) batched MAPF environment
+ * hot path + prioritized-replay sum-tree / TD kernels.
+ *
+ * This is the drop-in boundary.  The reference (ZiyuanMa/MAPF_RL) is pure Python and has no FFI;
+ * its boundary for this path is the duck-typed class `environment.Environment` and
+ * `buffer.SumTree` / `buffer.LocalBuffer`.  Every entry point below names the reference interface
+ * (file:line in /root/reference) it replaces.  The Python mirror of those classes
+ * (mapf_rl_b200/environment.py, mapf_rl_b200/buffer.py) binds exactly these symbols through ctypes;
+ * INTEGRATION.md shows the stub a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - plain C types only; no torch / CUDA types in signatures.  `stream` is a cudaStream_t passed as
+ *     void* (NULL = legacy default stream).
+ *   - every pointer named d_* is DEVICE memory owned by the caller; h_* is HOST memory.
+ *     The library never returns memory the caller must free; a handle owns only its state arena.
+ *   - all functions return 0 on success, a negative MAPF_E* code otherwise; mapf_last_error()
+ *     returns a thread-local message for the last failure.
+ *   - functions are asynchronous on `stream` unless documented otherwise; one handle must not be
+ *     used from two threads at once (the reference env is single-threaded, worker.py:355-361).
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point fails with
+ *     MAPF_ECUDA.
+ *
+ * Coordinates follow the reference: position (x, y) = (row, col) of map[x, y]; actions
+ * 0 stay, 1 up (x-1), 2 down (x+1), 3 left (y-1), 4 right (y+1)  (environment.py:12).
+ */
+#ifndef MAPF_B200_H
+#define MAPF_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MAPF_ABI_VERSION 1
+
+#define MAPF_OK 0
+#define MAPF_EINVAL (-1)   /* bad argument (shape, NULL, unsupported size)          */
+#define MAPF_ECUDA (-2)    /* CUDA runtime error / no device                         */
+#define MAPF_EACTION (-3)  /* an action was outside 0..4 (environment.py:289-290)    */
+#define MAPF_EUNIQUE (-4)  /* two agents share a cell (environment.py:424-428)       */
+#define MAPF_ENOMEM (-5)
+
+#define MAPF_OBS_RADIUS 4  /* config.py:14 — the only radius any reference consumer uses */
+#define MAPF_FOV 9
+#define MAPF_OBS_CHANNELS 6
+#define MAPF_OBS_BYTES_PER_AGENT 486 /* 6*9*9, config.py:7 obs_shape */
+#define MAPF_MAX_AGENTS 128
+#define MAPF_MAX_MAP_SIDE 120
+#define MAPF_DIST_UNREACHABLE 2147483647 /* environment.py:218 */
+
+typedef struct mapf_env mapf_env; /* opaque: a lockstep batch of B independent environments */
+typedef struct mapf_per mapf_per; /* opaque: one prioritized-replay sum tree               */
+
+typedef struct mapf_env_config {
+    int32_t num_envs;    /* B >= 1                                                          */
+    int32_t num_agents;  /* N, 1..MAPF_MAX_AGENTS          (environment.py:75 num_agents)   */
+    int32_t map_length;  /* L, 2..MAPF_MAX_MAP_SIDE, square (environment.py:75 map_length)  */
+    int32_t obs_radius;  /* must be 4                       (environment.py:76)             */
+    int32_t device;      /* CUDA device ordinal                                             */
+    /* reward_fn in the order move, stay_on_goal, stay_off_goal, collision, finish
+     * (config.py:8-12, environment.py:76,142) */
+    float reward_fn[5];
+} mapf_env_config;
+
+/* ---- lifetime ---------------------------------------------------------------------------- */
+int mapf_abi_version(void);
+const char *mapf_last_error(void);
+
+/* Environment.__init__ storage part (environment.py:75-144): allocates the device arena. */
+int mapf_env_create(const mapf_env_config *cfg, mapf_env **out);
+int mapf_env_destroy(mapf_env *env);
+/* bytes of device memory held by the handle */
+int64_t mapf_env_arena_bytes(const mapf_env *env);
+
+/* ---- Environment.load (environment.py:198-215) -------------------------------------------- */
+/* Loads `n` instances into the env slots listed in d_env_ids (NULL => slots 0..n-1), resets their
+ * step counters to 0 and recomputes their heuristic maps (get_navi_map, environment.py:217-276).
+ *   d_maps   u8[n, L, L]  0 = free, non-zero = obstacle
+ *   d_agents u8[n, N, 2]  (x, y);   d_goals u8[n, N, 2]                                   */
+int mapf_env_load(mapf_env *env, const int32_t *d_env_ids, int32_t n, const uint8_t *d_maps,
+                  const uint8_t *d_agents, const uint8_t *d_goals, void *stream);
+
+/* ---- Environment.get_navi_map (environment.py:217-276) / search.compute_heuristics
+ *      (search.py:24-55) -------------------------------------------------------------------- */
+/* Recomputes the per-agent BFS heuristic maps of the listed env slots (NULL => all B).
+ * d_dist_out (optional) receives the distance maps, i32[n, N, L, L], 2147483647 where
+ * unreachable / obstacle — the same numbers search.compute_heuristics returns where finite. */
+int mapf_env_bfs_navi(mapf_env *env, const int32_t *d_env_ids, int32_t n, int32_t *d_dist_out, void *stream);
+
+/* ---- Environment.step (environment.py:278-430), fused with the observe() it ends in (:430) -- */
+/*   d_actions  u8[B, N]          in
+ *   d_obs      u8[B, N, 6, 9, 9] out, bool bytes, layout of environment.py:444-465
+ *   d_rewards  f32[B, N]         out (the reference's python numbers cast to fp32)
+ *   d_done     u8[B]             out (environment.py:415-419)
+ *   d_steps    i32[B]            out, optional: env.steps after the step (environment.py:412)
+ * An action outside 0..4 is treated as "stay" and latches MAPF_EACTION (see mapf_env_status). */
+int mapf_env_step_observe(mapf_env *env, const uint8_t *d_actions, uint8_t *d_obs, float *d_rewards,
+                          uint8_t *d_done, int32_t *d_steps, void *stream);
+
+/* Environment.observe (environment.py:433-467).  d_pos (optional) u8[B, N, 2]. */
+int mapf_env_observe(mapf_env *env, uint8_t *d_obs, uint8_t *d_pos, void *stream);
+
+/* Host-buffer variant of step (what a per-process actor calls): copies actions H2D, runs the fused
+ * kernel, copies rewards / done / steps (and obs if h_obs != NULL) D2H, then synchronises.
+ * All h_* buffers are ordinary or pinned host memory.  d_obs_opt: if non-NULL the observation is
+ * written there (device replay tensor) instead of an internal buffer. */
+int mapf_env_step_host(mapf_env *env, const uint8_t *h_actions, uint8_t *h_obs, float *h_rewards,
+                       uint8_t *h_done, int32_t *h_steps, uint8_t *d_obs_opt, void *stream);
+
+/* ---- state access (attributes read by worker.py:390,426 / test.py:46-48,130) --------------- */
+/* Any output pointer may be NULL.  d_map u8[B,L,L]; d_pos/d_goals u8[B,N,2]; d_steps i32[B];
+ * d_navi u8[B,N,4,L,L] = navi_map without the obs_radius padding (environment.py:253-276). */
+int mapf_env_get_state(mapf_env *env, uint8_t *d_map, uint8_t *d_pos, uint8_t *d_goals, int32_t *d_steps,
+                       uint8_t *d_navi, void *stream);
+/* Overwrite agent positions / step counters (used to restore snapshots). Either may be NULL. */
+int mapf_env_set_state(mapf_env *env, const uint8_t *d_pos, const int32_t *d_steps, void *stream);
+
+/* Synchronous: returns the latched error (MAPF_OK, MAPF_EACTION, MAPF_EUNIQUE) and clears it. */
+int mapf_env_status(mapf_env *env, void *stream);
+
+/* ---- Environment.reset instance generation (environment.py:146-196), device side ----------- */
+/* Draws new random instances for the slots whose d_mask byte is non-zero (NULL => all): obstacle map
+ * iid Bernoulli(density) (density < 0 => one triangular(0, 0.33, 0.5) draw per env, :156), start and
+ * goal of every agent in one 4-connected free component (:159-192), steps = 0, heuristic maps
+ * recomputed.  Counter-based RNG: env slot e uses stream (seed, env_offset + e) so shards of a
+ * multi-GPU job draw the instances a single GPU would.  Distributional parity only. */
+int mapf_env_reset(mapf_env *env, const uint8_t *d_mask, uint64_t seed, uint64_t env_offset, float density,
+                   void *stream);
+
+/* ---- buffer.SumTree (buffer.py:16-105) ------------------------------------------------------ */
+/* capacity must be a power of two (buffer.py:23).  Tree nodes are fp64 like the reference. */
+int mapf_per_create(int64_t capacity, int32_t device, mapf_per **out);
+int mapf_per_destroy(mapf_per *tree);
+/* device pointer to the 2*capacity-1 fp64 nodes (SumTree.tree, buffer.py:25); leaves start at capacity-1 */
+double *mapf_per_tree_ptr(mapf_per *tree);
+
+/* SumTree.batch_update (buffer.py:95-105): leaf[d_idx[k]] = d_prio[k] (duplicates: last in batch order
+ * wins, numpy fancy assignment), then every touched ancestor = left + right, level by level.
+ * d_idx is NOT modified (the reference mutates it in place, buffer.py:96; the Python mirror
+ * reproduces that). */
+int mapf_per_update(mapf_per *tree, const int64_t *d_idx, const double *d_prio, int64_t n, void *stream);
+
+/* SumTree.batch_sample (buffer.py:56-78) with caller-supplied uniforms u in [0,1):
+ * prefix_i = i*interval + u_i*interval.  d_weight_out (optional) = (p / min_batch p)^(-beta)
+ * (worker.py:165-166). */
+int mapf_per_sample(mapf_per *tree, const double *d_uniforms, int64_t batch, int64_t *d_idx_out,
+                    double *d_prio_out, float *d_weight_out, double beta, void *stream);
+
+/* Fused learner tail (worker.py:300-308 + 186-203 + buffer.py:95-105), one call after the two
+ * Q-network forwards:
+ *   td      = Q(s,a) - (r + gamma^steps * (1-done) * max_a' Qtgt(s',a'))        (worker.py:302-306)
+ *             (d_q_online_next != NULL => double-Q: a* = argmax Q_online(s'), bootstrap Qtgt(s',a*))
+ *   prio    = max(|td|, 1e-6)                                                  (worker.py:308)
+ *   leaf    = prio^alpha for samples whose episode slot was not overwritten since sampling
+ *             (window [old_ptr, ptr) in units of slot_steps leaves, wrap-aware, worker.py:192-201)
+ *   then the ancestor refresh of batch_update.
+ * All fp32 inputs; tree in fp64.  d_td_out / d_prio_out f32[n] (either may be NULL). */
+int mapf_per_td_update(mapf_per *tree, const float *d_q_online, const float *d_q_target_next,
+                       const float *d_q_online_next, const int64_t *d_action, const float *d_reward,
+                       const float *d_done, const float *d_steps, const int64_t *d_idx, int64_t n, float gamma,
+                       double alpha, int64_t old_ptr, int64_t ptr, int64_t slot_steps, float *d_td_out,
+                       float *d_prio_out, void *stream);
+
+/* LocalBuffer.finish TD (buffer.py:170-177) for `episodes` episodes of up to `capacity` steps:
+ *   td[e,t] = | r[e,t] + 0.99*r[e,t+1] + max_a q[e,t,a] - q[e,t,act[e,t]] |,  0 for t >= size[e]
+ *   d_rew f32[episodes, capacity] (already rounded through fp16 by the caller, buffer.py:122),
+ *   d_q f32[episodes, capacity, 5], d_act u8[episodes, capacity], d_size i32[episodes],
+ *   d_td_out f64[episodes, capacity]. */
+int mapf_actor_td(const float *d_rew, const float *d_q, const uint8_t *d_act, const int32_t *d_size,
+                  int32_t episodes, int32_t capacity, double *d_td_out, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MAPF_B200_H */

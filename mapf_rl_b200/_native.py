@@ -1,0 +1,83 @@
+"""ctypes binding of libmapf_b200.so (include/mapf_b200.h).  No fallback: if the CUDA library is
+missing and cannot be built, importing a compute entry point raises."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+from . import build as _build
+
+_lib = None
+
+MAPF_OK, MAPF_EINVAL, MAPF_ECUDA, MAPF_EACTION, MAPF_EUNIQUE, MAPF_ENOMEM = 0, -1, -2, -3, -4, -5
+
+
+class EnvConfig(C.Structure):
+    _fields_ = [("num_envs", C.c_int32), ("num_agents", C.c_int32), ("map_length", C.c_int32),
+                ("obs_radius", C.c_int32), ("device", C.c_int32), ("reward_fn", C.c_float * 5)]
+
+
+# name -> (restype, argtypes); must list every symbol include/mapf_b200.h declares
+_vp, _i32, _i64, _f32, _f64, _u64 = C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.c_double, C.c_uint64
+SIGNATURES = {
+    "mapf_abi_version": (C.c_int, []),
+    "mapf_last_error": (C.c_char_p, []),
+    "mapf_env_create": (C.c_int, [C.POINTER(EnvConfig), C.POINTER(_vp)]),
+    "mapf_env_destroy": (C.c_int, [_vp]),
+    "mapf_env_arena_bytes": (_i64, [_vp]),
+    "mapf_env_load": (C.c_int, [_vp, _vp, _i32, _vp, _vp, _vp, _vp]),
+    "mapf_env_bfs_navi": (C.c_int, [_vp, _vp, _i32, _vp, _vp]),
+    "mapf_env_step_observe": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "mapf_env_observe": (C.c_int, [_vp, _vp, _vp, _vp]),
+    "mapf_env_step_host": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "mapf_env_get_state": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "mapf_env_set_state": (C.c_int, [_vp, _vp, _vp, _vp]),
+    "mapf_env_status": (C.c_int, [_vp, _vp]),
+    "mapf_env_reset": (C.c_int, [_vp, _vp, _u64, _u64, _f32, _vp]),
+    "mapf_per_create": (C.c_int, [_i64, _i32, C.POINTER(_vp)]),
+    "mapf_per_destroy": (C.c_int, [_vp]),
+    "mapf_per_tree_ptr": (_vp, [_vp]),
+    "mapf_per_update": (C.c_int, [_vp, _vp, _vp, _i64, _vp]),
+    "mapf_per_sample": (C.c_int, [_vp, _vp, _i64, _vp, _vp, _vp, _f64, _vp]),
+    "mapf_per_td_update": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _f32, _f64, _i64, _i64, _i64,
+                                     _vp, _vp, _vp]),
+    "mapf_actor_td": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _vp, _vp]),
+}
+
+
+class MapfError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"libmapf_b200 error {code}: {msg}")
+        self.code = code
+
+
+def lib():
+    """Load (building first if the in-tree .so is missing or stale and nvcc is present)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = _build.LIB_PATH
+    if _build.is_stale():
+        try:
+            _build.build()
+        except Exception as e:  # no nvcc on this box: use the shipped .so if there is one
+            if not os.path.exists(path):
+                raise ImportError(f"libmapf_b200.so is missing and could not be built ({e}); "
+                                  "there is no CPU fallback") from e
+    L = C.CDLL(path)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(L, name)  # AttributeError = ABI mismatch, fail loudly
+        fn.restype = res
+        fn.argtypes = args
+    if L.mapf_abi_version() != 1:
+        raise ImportError("libmapf_b200.so ABI version mismatch")
+    _lib = L
+    return L
+
+
+def check(code: int):
+    if code != MAPF_OK:
+        msg = lib().mapf_last_error().decode("utf-8", "replace")
+        if code == MAPF_EACTION:
+            raise AssertionError("action index out of range")  # environment.py:290
+        raise MapfError(code, msg)

@@ -1,0 +1,220 @@
+"""BatchedEnvironment — B lockstep MAPF environments resident on one B200.
+
+The fast path of this package: torch CUDA tensors in, torch CUDA tensors out, every call one or two
+launches of hand-written sm_100a kernels through the C ABI (include/mapf_b200.h).  Semantics per
+environment are exactly the reference's `Environment` (environment.py:74-467); the drop-in single-env
+class in `mapf_rl_b200.environment` is a B = 1 view of this one.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import numpy as np
+
+from . import _native, config
+
+
+def _torch():
+    import torch
+    return torch
+
+
+class BatchedEnvironment:
+    OBS_SHAPE = config.obs_shape  # (6, 9, 9)
+
+    def __init__(self, num_envs: int, num_agents: int = config.num_agents, map_length: int = config.map_length,
+                 device=None, obs_radius: int = config.obs_radius, reward_fn: dict = config.reward_fn):
+        torch = _torch()
+        if not torch.cuda.is_available():
+            raise RuntimeError("mapf_rl_b200 needs a CUDA device: the environment kernels have no CPU fallback")
+        self._lib = _native.lib()
+        self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
+        self.num_envs, self.num_agents, self.map_length = int(num_envs), int(num_agents), int(map_length)
+        self.map_size = (self.map_length, self.map_length)
+        self.obs_radius = int(obs_radius)
+        self.reward_fn = dict(reward_fn)
+        cfg = _native.EnvConfig(self.num_envs, self.num_agents, self.map_length, self.obs_radius, self.device.index,
+                                (C.c_float * 5)(*[float(self.reward_fn[k]) for k in config.REWARD_ORDER]))
+        h = C.c_void_p()
+        _native.check(self._lib.mapf_env_create(C.byref(cfg), C.byref(h)))
+        self._h = h
+        B, N = self.num_envs, self.num_agents
+        self._rewards = torch.empty((B, N), dtype=torch.float32, device=self.device)
+        self._done = torch.empty((B,), dtype=torch.uint8, device=self.device)
+        self._steps = torch.empty((B,), dtype=torch.int32, device=self.device)
+
+    # -- plumbing ------------------------------------------------------------------------------
+    def close(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            self._lib.mapf_env_destroy(h)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _stream(self):
+        return C.c_void_p(_torch().cuda.current_stream(self.device).cuda_stream)
+
+    def _dev_u8(self, x, shape, as_mask=False):
+        """Bring an array-like to a contiguous uint8 tensor on this device (as_mask: non-zero -> 1)."""
+        torch = _torch()
+        t = x if isinstance(x, torch.Tensor) else torch.as_tensor(np.ascontiguousarray(x))
+        if as_mask:
+            t = (t != 0)
+        t = t.to(device=self.device, dtype=torch.uint8).contiguous()
+        assert tuple(t.shape) == tuple(shape), f"expected shape {shape}, got {tuple(t.shape)}"
+        return t
+
+    @property
+    def arena_bytes(self) -> int:
+        return int(self._lib.mapf_env_arena_bytes(self._h))
+
+    # -- Environment.load (environment.py:198-215) ----------------------------------------------
+    def load(self, maps, agents_pos, goals_pos, env_ids=None):
+        """maps [n,L,L] (0 free / non-zero obstacle, any dtype), agents_pos / goals_pos [n,N,2].
+        env_ids: which slots to load (default 0..n-1).  Recomputes the heuristic maps of those slots."""
+        torch = _torch()
+        L, N = self.map_length, self.num_agents
+        n = int(maps.shape[0])
+        m = self._dev_u8(maps, (n, L, L), as_mask=True)
+        a = self._dev_u8(agents_pos, (n, N, 2))
+        g = self._dev_u8(goals_pos, (n, N, 2))
+        ids_ptr = None
+        if env_ids is not None:
+            ids = torch.as_tensor(env_ids, dtype=torch.int32).to(self.device).contiguous()
+            assert ids.numel() == n
+            ids_ptr = C.c_void_p(ids.data_ptr())
+        _native.check(self._lib.mapf_env_load(self._h, ids_ptr, n, C.c_void_p(m.data_ptr()), C.c_void_p(a.data_ptr()),
+                                              C.c_void_p(g.data_ptr()), self._stream()))
+        # keep inputs alive until the stream has consumed them
+        torch.cuda.current_stream(self.device).synchronize()
+
+    # -- Environment.reset generator, device side (environment.py:146-196) ----------------------
+    def reset(self, mask=None, seed: int = 0, env_offset: int = 0, density: Optional[float] = None):
+        """Draw new random instances on the device for slots with mask != 0 (default: all)."""
+        mptr = None
+        if mask is not None:
+            mk = self._dev_u8(mask, (self.num_envs,))
+            mptr = C.c_void_p(mk.data_ptr())
+        dens = -1.0 if density is None else float(density)
+        _native.check(self._lib.mapf_env_reset(self._h, mptr, C.c_uint64(seed), C.c_uint64(env_offset),
+                                               C.c_float(dens), self._stream()))
+
+    # -- Environment.step + observe (environment.py:278-467) -------------------------------------
+    def step(self, actions, out_obs=None, out_rewards=None, out_done=None):
+        """actions: uint8 CUDA tensor [B,N] (anything else is converted).
+        Returns (obs uint8[B,N,6,9,9], rewards float32[B,N], done uint8[B]); obs is written into
+        `out_obs` when given (e.g. a slot of a device replay tensor)."""
+        torch = _torch()
+        B, N = self.num_envs, self.num_agents
+        if not (isinstance(actions, torch.Tensor) and actions.dtype == torch.uint8 and actions.is_cuda
+                and actions.is_contiguous()):
+            actions = torch.as_tensor(np.asarray(actions) if not isinstance(actions, torch.Tensor) else actions)
+            actions = actions.to(device=self.device, dtype=torch.uint8).contiguous()
+        assert actions.shape == (B, N), "actions number"
+        obs = out_obs if out_obs is not None else torch.empty((B, N, *self.OBS_SHAPE), dtype=torch.uint8, device=self.device)
+        rewards = out_rewards if out_rewards is not None else self._rewards
+        done = out_done if out_done is not None else self._done
+        assert obs.is_contiguous() and obs.dtype == torch.uint8 and obs.numel() == B * N * 486
+        _native.check(self._lib.mapf_env_step_observe(self._h, C.c_void_p(actions.data_ptr()), C.c_void_p(obs.data_ptr()),
+                                                      C.c_void_p(rewards.data_ptr()), C.c_void_p(done.data_ptr()),
+                                                      C.c_void_p(self._steps.data_ptr()), self._stream()))
+        return obs, rewards, done
+
+    def observe(self, out_obs=None):
+        """-> (obs uint8[B,N,6,9,9], pos uint8[B,N,2])   (environment.py:433-467)"""
+        torch = _torch()
+        B, N = self.num_envs, self.num_agents
+        obs = out_obs if out_obs is not None else torch.empty((B, N, *self.OBS_SHAPE), dtype=torch.uint8, device=self.device)
+        pos = torch.empty((B, N, 2), dtype=torch.uint8, device=self.device)
+        _native.check(self._lib.mapf_env_observe(self._h, C.c_void_p(obs.data_ptr()), C.c_void_p(pos.data_ptr()),
+                                                 self._stream()))
+        return obs, pos
+
+    def step_host(self, actions: np.ndarray, want_obs: bool = False, device_obs=None):
+        """Host-buffer step through mapf_env_step_host: numpy in, numpy out, synchronous."""
+        B, N = self.num_envs, self.num_agents
+        a = np.ascontiguousarray(actions, dtype=np.uint8)
+        assert a.shape == (B, N), "actions number"
+        rewards = np.empty((B, N), dtype=np.float32)
+        done = np.empty((B,), dtype=np.uint8)
+        steps = np.empty((B,), dtype=np.int32)
+        obs = np.empty((B, N, *self.OBS_SHAPE), dtype=np.uint8) if want_obs else None
+        _native.check(self._lib.mapf_env_step_host(
+            self._h, a.ctypes.data_as(C.c_void_p), obs.ctypes.data_as(C.c_void_p) if want_obs else None,
+            rewards.ctypes.data_as(C.c_void_p), done.ctypes.data_as(C.c_void_p), steps.ctypes.data_as(C.c_void_p),
+            C.c_void_p(device_obs.data_ptr()) if device_obs is not None else None, self._stream()))
+        return obs, rewards, done, steps
+
+    def check(self):
+        """Synchronous: raise if a kernel latched an error (bad action -> AssertionError like the reference)."""
+        _native.check(self._lib.mapf_env_status(self._h, self._stream()))
+
+    # -- attributes (device tensors) -----------------------------------------------------------
+    def _get_state(self, want):
+        torch = _torch()
+        B, N, L = self.num_envs, self.num_agents, self.map_length
+        out = {}
+        shapes = dict(map=((B, L, L), torch.uint8), pos=((B, N, 2), torch.uint8), goals=((B, N, 2), torch.uint8),
+                      steps=((B,), torch.int32), navi=((B, N, 4, L, L), torch.uint8))
+        ptrs = []
+        for k in ("map", "pos", "goals", "steps", "navi"):
+            if k in want:
+                out[k] = torch.empty(shapes[k][0], dtype=shapes[k][1], device=self.device)
+                ptrs.append(C.c_void_p(out[k].data_ptr()))
+            else:
+                ptrs.append(None)
+        _native.check(self._lib.mapf_env_get_state(self._h, *ptrs, self._stream()))
+        return out
+
+    @property
+    def steps(self):
+        return self._get_state({"steps"})["steps"]
+
+    @property
+    def agents_pos(self):
+        return self._get_state({"pos"})["pos"]
+
+    @property
+    def goals_pos(self):
+        return self._get_state({"goals"})["goals"]
+
+    @property
+    def map(self):
+        return self._get_state({"map"})["map"]
+
+    @property
+    def navi_map(self):
+        """uint8[B,N,4,L,L]: navi_map without the obs_radius padding (environment.py:253-276)."""
+        return self._get_state({"navi"})["navi"]
+
+    def set_state(self, agents_pos=None, steps=None):
+        torch = _torch()
+        p = s = None
+        if agents_pos is not None:
+            p = self._dev_u8(agents_pos, (self.num_envs, self.num_agents, 2))
+        if steps is not None:
+            s = torch.as_tensor(steps, dtype=torch.int32).to(self.device).contiguous()
+        _native.check(self._lib.mapf_env_set_state(self._h, C.c_void_p(p.data_ptr()) if p is not None else None,
+                                                   C.c_void_p(s.data_ptr()) if s is not None else None, self._stream()))
+        torch.cuda.current_stream(self.device).synchronize()
+
+    def heuristic_distances(self, env_ids=None):
+        """Recompute the BFS maps and return int32[n,N,L,L] distances (2147483647 = unreachable);
+        equal to search.compute_heuristics (search.py:24-55) where finite."""
+        torch = _torch()
+        N, L = self.num_agents, self.map_length
+        ids_ptr, n = None, self.num_envs
+        if env_ids is not None:
+            ids = torch.as_tensor(env_ids, dtype=torch.int32).to(self.device).contiguous()
+            ids_ptr, n = C.c_void_p(ids.data_ptr()), int(ids.numel())
+        dist = torch.empty((n, N, L, L), dtype=torch.int32, device=self.device)
+        _native.check(self._lib.mapf_env_bfs_navi(self._h, ids_ptr, n, C.c_void_p(dist.data_ptr()), self._stream()))
+        torch.cuda.current_stream(self.device).synchronize()
+        return dist

@@ -1,0 +1,453 @@
+// mapf_abi.cu — extern "C" entry points of libmapf_b200.so (declared in include/mapf_b200.h).
+// Argument validation, arena ownership and stream plumbing only; the kernels live in
+// mapf_env_kernels.cu / mapf_reset_kernels.cu / mapf_per_kernels.cu.
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+#include "mapf_common.cuh"
+
+// launchers (other translation units)
+int mapf_launch_pack_load(mapf_env *, const int32_t *, int, const uint8_t *, const uint8_t *, const uint8_t *, cudaStream_t);
+int mapf_launch_bfs(mapf_env *, const int32_t *, int, int32_t *, cudaStream_t);
+int mapf_launch_step(mapf_env *, const uint8_t *, uint8_t *, float *, uint8_t *, int32_t *, cudaStream_t);
+int mapf_launch_observe(mapf_env *, uint8_t *, uint8_t *, cudaStream_t);
+int mapf_launch_unpack(mapf_env *, uint8_t *, uint8_t *, cudaStream_t);
+int mapf_launch_reset(mapf_env *, const uint8_t *, uint64_t, uint64_t, float, cudaStream_t);
+int mapf_launch_per_update(mapf_per *, PerScratch *, const int64_t *, const double *, int64_t, cudaStream_t);
+int mapf_launch_per_sample(mapf_per *, const double *, int64_t, int64_t *, double *, float *, double, cudaStream_t);
+int mapf_launch_per_td_update(mapf_per *, PerScratch *, const float *, const float *, const float *, const int64_t *,
+                              const float *, const float *, const float *, const int64_t *, int64_t, float, double, int64_t,
+                              int64_t, int64_t, float *, float *, cudaStream_t);
+int mapf_launch_actor_td(const float *, const float *, const uint8_t *, const int32_t *, int, int, double *, cudaStream_t);
+
+static thread_local std::string g_last_error;
+
+void mapf_set_error(const std::string &msg) { g_last_error = msg; }
+
+int mapf_cuda_fail(cudaError_t e, const char *what)
+{
+    g_last_error = std::string("CUDA error: ") + cudaGetErrorString(e) + " in " + what;
+    return MAPF_ECUDA;
+}
+
+namespace {
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = false;
+    explicit DeviceGuard(int dev)
+    {
+        if (cudaGetDevice(&prev) != cudaSuccess) return;
+        ok = (prev == dev) || cudaSetDevice(dev) == cudaSuccess;
+    }
+    ~DeviceGuard()
+    {
+        if (ok && prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+template <typename T>
+int dev_alloc(T **p, size_t count, int64_t *total)
+{
+    size_t bytes = count * sizeof(T);
+    if (bytes == 0) bytes = 16;
+    cudaError_t e = cudaMalloc(reinterpret_cast<void **>(p), bytes);
+    if (e != cudaSuccess) {
+        mapf_cuda_fail(e, "cudaMalloc");
+        return MAPF_ENOMEM;
+    }
+    *total += (int64_t)bytes;
+    return MAPF_OK;
+}
+}  // namespace
+
+extern "C" {
+
+int mapf_abi_version(void) { return MAPF_ABI_VERSION; }
+
+const char *mapf_last_error(void) { return g_last_error.c_str(); }
+
+int mapf_env_create(const mapf_env_config *cfg, mapf_env **out)
+{
+    if (!cfg || !out) {
+        mapf_set_error("mapf_env_create: NULL argument");
+        return MAPF_EINVAL;
+    }
+    *out = nullptr;
+    if (cfg->num_envs < 1 || cfg->num_agents < 1 || cfg->num_agents > MAPF_MAX_AGENTS || cfg->map_length < 2 ||
+        cfg->map_length > MAPF_MAX_MAP_SIDE) {
+        mapf_set_error("mapf_env_create: num_envs >= 1, 1 <= num_agents <= 128, 2 <= map_length <= 120 required");
+        return MAPF_EINVAL;
+    }
+    if (cfg->obs_radius != MAPF_OBS_RADIUS) {
+        mapf_set_error("mapf_env_create: only obs_radius = 4 is supported (config.py:14)");
+        return MAPF_EINVAL;
+    }
+    if ((int64_t)cfg->num_agents > (int64_t)cfg->map_length * cfg->map_length) {
+        mapf_set_error("mapf_env_create: more agents than cells");
+        return MAPF_EINVAL;
+    }
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        mapf_set_error("mapf_env_create: no CUDA device (this library has no CPU fallback)");
+        return MAPF_ECUDA;
+    }
+    if (cfg->device < 0 || cfg->device >= ndev) {
+        mapf_set_error("mapf_env_create: bad device ordinal");
+        return MAPF_EINVAL;
+    }
+    DeviceGuard guard(cfg->device);
+    if (!guard.ok) {
+        mapf_set_error("mapf_env_create: cudaSetDevice failed");
+        return MAPF_ECUDA;
+    }
+    mapf_env *env = new (std::nothrow) mapf_env();
+    if (!env) return MAPF_ENOMEM;
+    std::memset(env, 0, sizeof(*env));
+    EnvDims &d = env->d;
+    d.B = cfg->num_envs;
+    d.N = cfg->num_agents;
+    d.L = cfg->map_length;
+    d.R = d.L + 8;
+    d.RW = (d.L + 8 + 31) / 32;
+    d.RWS = d.RW + 1;
+    d.CB = (d.L + 8 + 7) / 8;
+    d.K = (d.N + 31) / 32;
+    d.obst_stride = (d.R * d.RWS + 3) & ~3;
+    d.navi_agent_stride = d.CB * d.R;
+    env->device = cfg->device;
+    for (int i = 0; i < 5; ++i) env->reward[i] = cfg->reward_fn[i];
+
+    int rc = MAPF_OK;
+    int64_t total = 0;
+    const size_t BN = (size_t)d.B * d.N;
+    if (rc == MAPF_OK) rc = dev_alloc(&env->obst, (size_t)d.B * d.obst_stride, &total);
+    if (rc == MAPF_OK) rc = dev_alloc(&env->pos, BN * 2, &total);
+    if (rc == MAPF_OK) rc = dev_alloc(&env->goal, BN * 2, &total);
+    if (rc == MAPF_OK) rc = dev_alloc(&env->navi, BN * d.navi_agent_stride, &total);
+    if (rc == MAPF_OK) rc = dev_alloc(&env->steps, (size_t)d.B, &total);
+    if (rc == MAPF_OK) rc = dev_alloc(&env->err, 1, &total);
+    if (rc == MAPF_OK) {
+        cudaError_t e2 = cudaMemset(env->obst, 0, (size_t)d.B * d.obst_stride * 4);
+        if (e2 == cudaSuccess) e2 = cudaMemset(env->pos, 0, BN * 2);
+        if (e2 == cudaSuccess) e2 = cudaMemset(env->goal, 0, BN * 2);
+        if (e2 == cudaSuccess) e2 = cudaMemset(env->navi, 0, BN * d.navi_agent_stride * 4);
+        if (e2 == cudaSuccess) e2 = cudaMemset(env->steps, 0, (size_t)d.B * 4);
+        if (e2 == cudaSuccess) e2 = cudaMemset(env->err, 0, 4);
+        if (e2 == cudaSuccess) e2 = cudaDeviceSynchronize();
+        if (e2 != cudaSuccess) rc = mapf_cuda_fail(e2, "cudaMemset(arena)");
+    }
+    env->arena_bytes = total;
+    if (rc != MAPF_OK) {
+        mapf_env_destroy(env);
+        return rc;
+    }
+    *out = env;
+    return MAPF_OK;
+}
+
+int mapf_env_destroy(mapf_env *env)
+{
+    if (!env) return MAPF_OK;
+    DeviceGuard guard(env->device);
+    cudaFree(env->obst);
+    cudaFree(env->pos);
+    cudaFree(env->goal);
+    cudaFree(env->navi);
+    cudaFree(env->steps);
+    cudaFree(env->err);
+    cudaFree(env->d_actions);
+    cudaFree(env->d_obs);
+    cudaFree(env->d_rewards);
+    cudaFree(env->d_done);
+    cudaFree(env->d_steps_out);
+    if (env->h_pinned) cudaFreeHost(env->h_pinned);
+    delete env;
+    return MAPF_OK;
+}
+
+int64_t mapf_env_arena_bytes(const mapf_env *env) { return env ? env->arena_bytes : 0; }
+
+#define REQUIRE_ENV(env)                          \
+    if (!(env)) {                                 \
+        mapf_set_error("NULL environment handle"); \
+        return MAPF_EINVAL;                       \
+    }                                             \
+    DeviceGuard guard((env)->device);             \
+    if (!guard.ok) {                              \
+        mapf_set_error("cudaSetDevice failed");   \
+        return MAPF_ECUDA;                        \
+    }
+
+int mapf_env_load(mapf_env *env, const int32_t *d_env_ids, int32_t n, const uint8_t *d_maps, const uint8_t *d_agents,
+                  const uint8_t *d_goals, void *stream)
+{
+    REQUIRE_ENV(env);
+    if (n < 0 || n > env->d.B || !d_maps || !d_agents || !d_goals) {
+        mapf_set_error("mapf_env_load: bad arguments");
+        return MAPF_EINVAL;
+    }
+    if (n == 0) return MAPF_OK;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    int rc = mapf_launch_pack_load(env, d_env_ids, n, d_maps, d_agents, d_goals, st);
+    if (rc != MAPF_OK) return rc;
+    return mapf_launch_bfs(env, d_env_ids, n, nullptr, st);
+}
+
+int mapf_env_bfs_navi(mapf_env *env, const int32_t *d_env_ids, int32_t n, int32_t *d_dist_out, void *stream)
+{
+    REQUIRE_ENV(env);
+    if (!d_env_ids) n = env->d.B;
+    if (n < 0 || n > env->d.B) {
+        mapf_set_error("mapf_env_bfs_navi: bad n");
+        return MAPF_EINVAL;
+    }
+    if (n == 0) return MAPF_OK;
+    return mapf_launch_bfs(env, d_env_ids, n, d_dist_out, static_cast<cudaStream_t>(stream));
+}
+
+int mapf_env_step_observe(mapf_env *env, const uint8_t *d_actions, uint8_t *d_obs, float *d_rewards, uint8_t *d_done,
+                          int32_t *d_steps, void *stream)
+{
+    REQUIRE_ENV(env);
+    if (!d_actions || !d_obs || !d_rewards || !d_done) {
+        mapf_set_error("mapf_env_step_observe: NULL buffer");
+        return MAPF_EINVAL;
+    }
+    return mapf_launch_step(env, d_actions, d_obs, d_rewards, d_done, d_steps, static_cast<cudaStream_t>(stream));
+}
+
+int mapf_env_observe(mapf_env *env, uint8_t *d_obs, uint8_t *d_pos, void *stream)
+{
+    REQUIRE_ENV(env);
+    if (!d_obs) {
+        mapf_set_error("mapf_env_observe: NULL buffer");
+        return MAPF_EINVAL;
+    }
+    return mapf_launch_observe(env, d_obs, d_pos, static_cast<cudaStream_t>(stream));
+}
+
+int mapf_env_step_host(mapf_env *env, const uint8_t *h_actions, uint8_t *h_obs, float *h_rewards, uint8_t *h_done,
+                       int32_t *h_steps, uint8_t *d_obs_opt, void *stream)
+{
+    REQUIRE_ENV(env);
+    if (!h_actions || !h_rewards || !h_done) {
+        mapf_set_error("mapf_env_step_host: NULL buffer");
+        return MAPF_EINVAL;
+    }
+    const EnvDims &d = env->d;
+    const size_t BN = (size_t)d.B * d.N;
+    int64_t total = env->arena_bytes;
+    int rc = MAPF_OK;
+    if (!env->d_actions) {
+        if (rc == MAPF_OK) rc = dev_alloc(&env->d_actions, BN, &total);
+        if (rc == MAPF_OK) rc = dev_alloc(&env->d_rewards, BN, &total);
+        if (rc == MAPF_OK) rc = dev_alloc(&env->d_done, (size_t)d.B, &total);
+        if (rc == MAPF_OK) rc = dev_alloc(&env->d_steps_out, (size_t)d.B, &total);
+        if (rc == MAPF_OK) {
+            cudaError_t e = cudaMallocHost(reinterpret_cast<void **>(&env->h_pinned), BN + BN * 4 + (size_t)d.B * 5 + 64);
+            if (e != cudaSuccess) rc = mapf_cuda_fail(e, "cudaMallocHost");
+        }
+    }
+    if (rc == MAPF_OK && !d_obs_opt && !env->d_obs) rc = dev_alloc(&env->d_obs, BN * MAPF_OBS_BYTES_PER_AGENT, &total);
+    env->arena_bytes = total;
+    if (rc != MAPF_OK) return rc;
+
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    uint8_t *obs_dev = d_obs_opt ? d_obs_opt : env->d_obs;
+    // pinned layout: actions u8[BN] | pad to 4 | rewards f32[BN] | steps i32[B] | done u8[B]
+    uint8_t *pin_act = env->h_pinned;
+    float *pin_rew = reinterpret_cast<float *>(env->h_pinned + ((BN + 15) & ~(size_t)15));
+    int32_t *pin_steps = reinterpret_cast<int32_t *>(pin_rew + BN);
+    uint8_t *pin_done = reinterpret_cast<uint8_t *>(pin_steps + d.B);
+    std::memcpy(pin_act, h_actions, BN);
+    MAPF_CUDA(cudaMemcpyAsync(env->d_actions, pin_act, BN, cudaMemcpyHostToDevice, st));
+    rc = mapf_launch_step(env, env->d_actions, obs_dev, env->d_rewards, env->d_done, env->d_steps_out, st);
+    if (rc != MAPF_OK) return rc;
+    MAPF_CUDA(cudaMemcpyAsync(pin_rew, env->d_rewards, BN * 4, cudaMemcpyDeviceToHost, st));
+    MAPF_CUDA(cudaMemcpyAsync(pin_steps, env->d_steps_out, (size_t)d.B * 4, cudaMemcpyDeviceToHost, st));
+    MAPF_CUDA(cudaMemcpyAsync(pin_done, env->d_done, (size_t)d.B, cudaMemcpyDeviceToHost, st));
+    if (h_obs) MAPF_CUDA(cudaMemcpyAsync(h_obs, obs_dev, BN * MAPF_OBS_BYTES_PER_AGENT, cudaMemcpyDeviceToHost, st));
+    MAPF_CUDA(cudaStreamSynchronize(st));
+    std::memcpy(h_rewards, pin_rew, BN * 4);
+    std::memcpy(h_done, pin_done, (size_t)d.B);
+    if (h_steps) std::memcpy(h_steps, pin_steps, (size_t)d.B * 4);
+    return MAPF_OK;
+}
+
+int mapf_env_get_state(mapf_env *env, uint8_t *d_map, uint8_t *d_pos, uint8_t *d_goals, int32_t *d_steps, uint8_t *d_navi,
+                       void *stream)
+{
+    REQUIRE_ENV(env);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const size_t BN2 = (size_t)env->d.B * env->d.N * 2;
+    if (d_pos) MAPF_CUDA(cudaMemcpyAsync(d_pos, env->pos, BN2, cudaMemcpyDeviceToDevice, st));
+    if (d_goals) MAPF_CUDA(cudaMemcpyAsync(d_goals, env->goal, BN2, cudaMemcpyDeviceToDevice, st));
+    if (d_steps) MAPF_CUDA(cudaMemcpyAsync(d_steps, env->steps, (size_t)env->d.B * 4, cudaMemcpyDeviceToDevice, st));
+    return mapf_launch_unpack(env, d_map, d_navi, st);
+}
+
+int mapf_env_set_state(mapf_env *env, const uint8_t *d_pos, const int32_t *d_steps, void *stream)
+{
+    REQUIRE_ENV(env);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (d_pos) MAPF_CUDA(cudaMemcpyAsync(env->pos, d_pos, (size_t)env->d.B * env->d.N * 2, cudaMemcpyDeviceToDevice, st));
+    if (d_steps) MAPF_CUDA(cudaMemcpyAsync(env->steps, d_steps, (size_t)env->d.B * 4, cudaMemcpyDeviceToDevice, st));
+    return MAPF_OK;
+}
+
+int mapf_env_status(mapf_env *env, void *stream)
+{
+    REQUIRE_ENV(env);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    int32_t bits = 0;
+    MAPF_CUDA(cudaMemcpyAsync(&bits, env->err, 4, cudaMemcpyDeviceToHost, st));
+    MAPF_CUDA(cudaStreamSynchronize(st));
+    if (bits) {
+        MAPF_CUDA(cudaMemsetAsync(env->err, 0, 4, st));
+        MAPF_CUDA(cudaStreamSynchronize(st));
+    }
+    if (bits & MAPF_ERRBIT_ACTION) {
+        mapf_set_error("action index out of range");
+        return MAPF_EACTION;
+    }
+    if (bits & MAPF_ERRBIT_UNIQUE) {
+        mapf_set_error("unique");
+        return MAPF_EUNIQUE;
+    }
+    return MAPF_OK;
+}
+
+int mapf_env_reset(mapf_env *env, const uint8_t *d_mask, uint64_t seed, uint64_t env_offset, float density, void *stream)
+{
+    REQUIRE_ENV(env);
+    if (density >= 1.0f) {
+        mapf_set_error("mapf_env_reset: density must be < 1");
+        return MAPF_EINVAL;
+    }
+    return mapf_launch_reset(env, d_mask, seed, env_offset, density, static_cast<cudaStream_t>(stream));
+}
+
+/* ---------------------------------------------------------------------------------------------- */
+
+int mapf_per_create(int64_t capacity, int32_t device, mapf_per **out)
+{
+    if (!out || capacity < 1 || (capacity & (capacity - 1)) != 0) {
+        mapf_set_error("buffer size only support power of 2 size");  // buffer.py:23
+        return MAPF_EINVAL;
+    }
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        mapf_set_error("mapf_per_create: no CUDA device (this library has no CPU fallback)");
+        return MAPF_ECUDA;
+    }
+    if (device < 0 || device >= ndev) {
+        mapf_set_error("mapf_per_create: bad device ordinal");
+        return MAPF_EINVAL;
+    }
+    DeviceGuard guard(device);
+    mapf_per *t = new (std::nothrow) mapf_per();
+    if (!t) return MAPF_ENOMEM;
+    std::memset(t, 0, sizeof(*t));
+    t->capacity = capacity;
+    t->device = device;
+    int layer = 1;
+    while ((int64_t(1) << (layer - 1)) < capacity) ++layer;  // buffer.py:20-22
+    t->layer = layer;
+    int64_t total = 0;
+    const int64_t nodes = 2 * capacity - 1;
+    t->scratch.cap_n = 1 << 16;
+    int rc = dev_alloc(&t->tree, (size_t)nodes, &total);
+    if (rc == MAPF_OK) rc = dev_alloc(&t->scratch.stamps, (size_t)capacity, &total);
+    if (rc == MAPF_OK) rc = dev_alloc(&t->scratch.prio32, (size_t)t->scratch.cap_n, &total);
+    if (rc == MAPF_OK) rc = dev_alloc(&t->scratch.active, (size_t)t->scratch.cap_n, &total);
+    if (rc == MAPF_OK) {
+        cudaError_t e = cudaMemset(t->tree, 0, (size_t)nodes * 8);
+        if (e == cudaSuccess) e = cudaMemset(t->scratch.stamps, 0, (size_t)capacity * 8);
+        if (e == cudaSuccess) e = cudaDeviceSynchronize();
+        if (e != cudaSuccess) rc = mapf_cuda_fail(e, "cudaMemset(tree)");
+    }
+    if (rc != MAPF_OK) {
+        mapf_per_destroy(t);
+        return rc;
+    }
+    *out = t;
+    return MAPF_OK;
+}
+
+int mapf_per_destroy(mapf_per *t)
+{
+    if (!t) return MAPF_OK;
+    DeviceGuard guard(t->device);
+    cudaFree(t->tree);
+    cudaFree(t->scratch.stamps);
+    cudaFree(t->scratch.prio32);
+    cudaFree(t->scratch.active);
+    delete t;
+    return MAPF_OK;
+}
+
+double *mapf_per_tree_ptr(mapf_per *t) { return t ? t->tree : nullptr; }
+
+#define REQUIRE_PER(t)                          \
+    if (!(t)) {                                 \
+        mapf_set_error("NULL sum-tree handle"); \
+        return MAPF_EINVAL;                     \
+    }                                           \
+    DeviceGuard guard((t)->device);             \
+    if (!guard.ok) {                            \
+        mapf_set_error("cudaSetDevice failed"); \
+        return MAPF_ECUDA;                      \
+    }
+
+int mapf_per_update(mapf_per *t, const int64_t *d_idx, const double *d_prio, int64_t n, void *stream)
+{
+    REQUIRE_PER(t);
+    if (n < 0 || (n > 0 && (!d_idx || !d_prio))) {
+        mapf_set_error("mapf_per_update: bad arguments");
+        return MAPF_EINVAL;
+    }
+    return mapf_launch_per_update(t, &t->scratch, d_idx, d_prio, n, static_cast<cudaStream_t>(stream));
+}
+
+int mapf_per_sample(mapf_per *t, const double *d_uniforms, int64_t batch, int64_t *d_idx_out, double *d_prio_out,
+                    float *d_weight_out, double beta, void *stream)
+{
+    REQUIRE_PER(t);
+    if (batch < 1 || !d_uniforms || !d_idx_out || !d_prio_out) {
+        mapf_set_error("mapf_per_sample: bad arguments");
+        return MAPF_EINVAL;
+    }
+    return mapf_launch_per_sample(t, d_uniforms, batch, d_idx_out, d_prio_out, d_weight_out, beta,
+                                  static_cast<cudaStream_t>(stream));
+}
+
+int mapf_per_td_update(mapf_per *t, const float *d_q_online, const float *d_q_target_next, const float *d_q_online_next,
+                       const int64_t *d_action, const float *d_reward, const float *d_done, const float *d_steps,
+                       const int64_t *d_idx, int64_t n, float gamma, double alpha, int64_t old_ptr, int64_t ptr,
+                       int64_t slot_steps, float *d_td_out, float *d_prio_out, void *stream)
+{
+    REQUIRE_PER(t);
+    if (n < 0 || n > t->scratch.cap_n || (n > 0 && (!d_q_online || !d_q_target_next || !d_action || !d_reward || !d_done ||
+                                                    !d_steps || !d_idx))) {
+        mapf_set_error("mapf_per_td_update: bad arguments (n <= 65536)");
+        return MAPF_EINVAL;
+    }
+    return mapf_launch_per_td_update(t, &t->scratch, d_q_online, d_q_target_next, d_q_online_next, d_action, d_reward, d_done,
+                                     d_steps, d_idx, n, gamma, alpha, old_ptr, ptr, slot_steps, d_td_out, d_prio_out,
+                                     static_cast<cudaStream_t>(stream));
+}
+
+int mapf_actor_td(const float *d_rew, const float *d_q, const uint8_t *d_act, const int32_t *d_size, int32_t episodes,
+                  int32_t capacity, double *d_td_out, void *stream)
+{
+    if (episodes < 0 || capacity < 1 || (episodes > 0 && (!d_rew || !d_q || !d_act || !d_size || !d_td_out))) {
+        mapf_set_error("mapf_actor_td: bad arguments");
+        return MAPF_EINVAL;
+    }
+    return mapf_launch_actor_td(d_rew, d_q, d_act, d_size, episodes, capacity, d_td_out, static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

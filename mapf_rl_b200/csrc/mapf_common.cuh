@@ -1,0 +1,85 @@
+// mapf_common.cuh — shared declarations of libmapf_b200.so (sm_100a only).
+//
+// Device data layout of one environment batch (all owned by the mapf_env handle):
+//
+//   obst   u32[B][obst_stride]      obstacle bitmap.  Row r of the PADDED grid (R = L + 8 rows, the
+//                                   obs_radius = 4 border included) occupies RWS = RW + 1 words, bit p of
+//                                   the row = padded column p (cell column y is bit y + 4).  Border rows /
+//                                   columns and the extra word are zero, so a 9-wide window is always a
+//                                   two-word funnel shift with no bounds checks (outside the map = 0,
+//                                   environment.py:447).
+//   pos    u8[B][N][2], goal u8[B][N][2]   (x, y) = (row, col)
+//   navi   u32[B][N][CB][R]         heuristic bits (environment.py:253-276).  Word [cb][r] holds, for padded
+//                                   row r and the 8 padded columns 8*cb .. 8*cb+7, one byte per direction
+//                                   d = 0 up, 1 down, 2 left, 3 right (byte d, bit c = column 8*cb + c).
+//                                   A 9x9 window therefore reads two runs of 9 consecutive words.
+//   steps  i32[B]
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+
+#include "../../include/mapf_b200.h"
+
+#define MAPF_FULL_MASK 0xffffffffu
+
+struct EnvDims {
+    int B, N, L;
+    int R;            // L + 8 padded rows
+    int RW;           // words holding the L + 8 padded column bits
+    int RWS;          // RW + 1: row stride in words
+    int CB;           // ceil((L + 8) / 8) column blocks
+    int K;            // ceil(N / 32) agent slots per lane
+    int obst_stride;  // words per env in `obst` (R * RWS rounded up to 4)
+    int navi_agent_stride;  // CB * R words per agent
+};
+
+struct mapf_env {
+    EnvDims d;
+    int device;
+    float reward[5];
+    uint32_t *obst;
+    uint8_t *pos;
+    uint8_t *goal;
+    uint32_t *navi;
+    int32_t *steps;
+    int32_t *err;      // latched device error bits
+    // staging for the host-buffer entry point
+    uint8_t *d_actions;
+    uint8_t *d_obs;
+    float *d_rewards;
+    uint8_t *d_done;
+    int32_t *d_steps_out;
+    uint8_t *h_pinned;  // pinned staging: actions | rewards | done | steps
+    int64_t arena_bytes;
+};
+
+// scratch owned by a tree handle
+struct PerScratch {
+    unsigned long long *stamps;  // u64[capacity]: (epoch << 32 | batch position + 1) of the last claimant
+    float *prio32;               // f32[cap_n]
+    uint8_t *active;             // u8[cap_n]
+    int64_t cap_n;
+    unsigned long long epoch;
+};
+
+struct mapf_per {
+    int64_t capacity;
+    int layer;
+    int device;
+    double *tree;
+    PerScratch scratch;
+};
+
+void mapf_set_error(const std::string &msg);
+int mapf_cuda_fail(cudaError_t e, const char *what);
+
+#define MAPF_CUDA(expr)                                        \
+    do {                                                       \
+        cudaError_t _e = (expr);                               \
+        if (_e != cudaSuccess) return mapf_cuda_fail(_e, #expr); \
+    } while (0)
+
+#define MAPF_ERRBIT_ACTION 1
+#define MAPF_ERRBIT_UNIQUE 2

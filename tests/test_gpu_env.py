@@ -1,0 +1,264 @@
+"""GPU parity: the CUDA environment path (through the C ABI) against the golden vectors from the live
+reference and against the C oracle on identical seeded inputs.  Bit-exact: positions, rewards (fp32),
+done, observation bytes, heuristic maps, distances."""
+import hashlib
+
+import numpy as np
+import pytest
+
+from helpers import golden, greedy_actions, instances, random_instance
+from oracle import oracle
+
+pytestmark = pytest.mark.gpu
+
+
+def sha8(b):
+    return np.frombuffer(hashlib.sha256(b).digest()[:8], dtype=np.uint64)[0]
+
+
+def make_env(B, N, L):
+    from mapf_rl_b200 import BatchedEnvironment
+    return BatchedEnvironment(B, N, L)
+
+
+def test_native_library_loaded():
+    import torch
+    from mapf_rl_b200 import _native, build
+    assert torch.cuda.is_available()
+    _native.lib()
+    with open("/proc/self/maps") as f:
+        assert build.LIB_PATH in f.read()
+
+
+def test_crafted_cases():
+    z = golden("crafted.npz")
+    for name in z["names"]:
+        m, a, g = z[f"{name}_map"], z[f"{name}_agents"], z[f"{name}_goals"]
+        env = make_env(1, a.shape[0], m.shape[0])
+        env.load(m[None], a[None], g[None])
+        obs, rew, done = env.step(z[f"{name}_actions"][None])
+        assert np.array_equal(env.agents_pos[0].cpu().numpy(), z[f"{name}_pos"]), name
+        assert np.array_equal(rew[0].cpu().numpy(), z[f"{name}_rewards"]), name
+        assert int(done[0]) == z[f"{name}_done"], name
+        assert np.array_equal(obs[0].cpu().numpy(), z[f"{name}_obs"]), name
+        obs, rew, done = env.step(np.zeros((1, a.shape[0]), dtype=np.uint8))
+        assert np.array_equal(rew[0].cpu().numpy(), z[f"{name}_rewards2"]), name
+        assert int(done[0]) == z[f"{name}_done2"]
+        assert int(env.steps[0]) - 1 == z[f"{name}_info2"]
+        env.check()
+
+
+@pytest.mark.parametrize("N", [16, 32, 64])
+@pytest.mark.parametrize("stream", ["U", "G"])
+def test_golden_traces(N, stream):
+    z = golden("traces.npz")
+    maps, agents, goals = instances(N)
+    pre = f"n{N}_{stream}_"
+    ks = z[pre + "instances"]
+    env = make_env(len(ks), N, 40)
+    env.load(maps[ks], agents[ks], goals[ks])
+    obs, pos = env.observe()
+    obs, pos = obs.cpu().numpy(), pos.cpu().numpy()
+    for q in range(len(ks)):
+        assert np.array_equal(pos[q], z[pre + "pos"][q, 0])
+        assert sha8(obs[q].tobytes()) == z[pre + "obs_sha8"][q, 0]
+    T = z[pre + "actions"].shape[1]
+    for s in range(T):
+        obs, rew, done = env.step(np.ascontiguousarray(z[pre + "actions"][:, s]))
+        obs, rew, done = obs.cpu().numpy(), rew.cpu().numpy(), done.cpu().numpy()
+        pos = env.agents_pos.cpu().numpy()
+        for q in range(len(ks)):
+            assert np.array_equal(pos[q], z[pre + "pos"][q, s + 1]), (q, s)
+            assert np.array_equal(rew[q], z[pre + "rewards"][q, s]), (q, s)
+            assert done[q] == z[pre + "done"][q, s]
+            assert sha8(obs[q].tobytes()) == z[pre + "obs_sha8"][q, s + 1], (q, s)
+    assert np.array_equal(env.steps.cpu().numpy(), np.full(len(ks), T))
+    env.check()
+
+
+@pytest.mark.parametrize("N", [16, 32, 64])
+def test_navi_all_pkl_instances(N):
+    z = golden("navi.npz")
+    maps, agents, goals = instances(N)
+    env = make_env(200, N, 40)
+    env.load(maps, agents, goals)
+    nv = env.navi_map.cpu().numpy()
+    for k in range(200):
+        got = np.frombuffer(hashlib.sha256(nv[k].tobytes()).digest(), dtype=np.uint8)
+        assert np.array_equal(got, z[f"navi{N}_sha256"][k]), k
+    assert np.array_equal(env.map.cpu().numpy(), maps)
+    assert np.array_equal(env.goals_pos.cpu().numpy(), goals)
+
+
+def test_distances_vs_compute_heuristics():
+    z = golden("navi.npz")
+    maps, agents, goals = instances(32)
+    env = make_env(200, 32, 40)
+    env.load(maps, agents, goals)
+    dist = env.heuristic_distances(env_ids=[0, 199]).cpu().numpy()
+    assert np.array_equal(dist[0], z["dist32_0"])
+    assert np.array_equal(dist[1], z["dist32_199"])
+    # recomputing must leave the heuristic maps unchanged
+    nv = env.navi_map.cpu().numpy()
+    got = np.frombuffer(hashlib.sha256(nv[199].tobytes()).digest(), dtype=np.uint8)
+    assert np.array_equal(got, z["navi32_sha256"][199])
+
+
+@pytest.mark.parametrize("N", [16, 32, 64])
+@pytest.mark.parametrize("stream", ["U", "G"])
+def test_full_pkl_rollout_vs_oracle(N, stream):
+    """All 200 instances x 256 steps (config.max_steps), every step compared with the C oracle."""
+    maps, agents, goals = instances(N)
+    B, T = 200, 256
+    env = make_env(B, N, 40)
+    env.load(maps, agents, goals)
+    ora = []
+    for k in range(B):
+        o = oracle.OracleEnv()
+        o.load(maps[k], agents[k], goals[k])
+        ora.append(o)
+    rng = np.random.default_rng(2024 + N)
+    obs, pos = env.observe()
+    obs = obs.cpu().numpy()
+    for k in range(B):
+        oo, op = ora[k].observe()
+        assert np.array_equal(oo.astype(np.uint8), obs[k])
+    collisions = 0
+    for s in range(T):
+        acts = rng.integers(0, 5, size=(B, N)).astype(np.uint8) if stream == "U" else greedy_actions(obs, rng)
+        g_obs, g_rew, g_done = env.step(acts)
+        obs, g_rew, g_done = g_obs.cpu().numpy(), g_rew.cpu().numpy(), g_done.cpu().numpy()
+        g_pos = env.agents_pos.cpu().numpy()
+        for k in range(B):
+            (o_obs, o_pos), o_rew, o_done, info = ora[k].step(acts[k])
+            assert np.array_equal(o_pos, g_pos[k]), (k, s)
+            assert np.array_equal(np.asarray(o_rew, dtype=np.float32), g_rew[k]), (k, s)
+            assert int(o_done) == g_done[k], (k, s)
+            assert np.array_equal(o_obs.astype(np.uint8), obs[k]), (k, s)
+        collisions += int((g_rew == -0.5).sum())
+        # invariant of environment.py:424-428
+        cells = g_pos[..., 0].astype(np.int32) * 40 + g_pos[..., 1]
+        assert all(len(np.unique(c)) == N for c in cells)
+    assert collisions > 0
+    env.check()
+
+
+@pytest.mark.parametrize("L,N,density,occupancy", [
+    (3, 5, 0.0, None), (4, 9, 0.1, None), (6, 30, 0.0, None), (8, 33, 0.05, None), (12, 64, 0.1, None),
+    (10, 7, 0.3, None), (20, 6, 0.3, None), (33, 37, 0.25, None), (56, 40, 0.3, None), (57, 12, 0.3, None),
+    (80, 64, 0.3, None), (88, 100, 0.2, None), (89, 8, 0.3, None), (120, 128, 0.1, None), (7, 45, 0.0, None),
+])
+def test_random_grids_vs_oracle(L, N, density, occupancy):
+    """Generic sizes: every RW (row words) / K (agents per lane) template, unaligned observation blocks,
+    dense boards (heavy swap / vertex / chain conflicts) and all-same-direction streams."""
+    rng = np.random.default_rng(L * 1000 + N)
+    B, T = 24, 40
+    ms, as_, gs = [], [], []
+    for _ in range(B):
+        m, a, g = random_instance(rng, L, N, density)
+        ms.append(m), as_.append(a), gs.append(g)
+    ms, as_, gs = np.stack(ms), np.stack(as_), np.stack(gs)
+    if B > 2:
+        gs[1] = as_[1]  # everyone starts on its goal: exercises finish / stay_on_goal
+    env = make_env(B, N, L)
+    env.load(ms, as_, gs)
+    nv = env.navi_map.cpu().numpy()
+    ora = []
+    for k in range(B):
+        o = oracle.OracleEnv()
+        o.load(ms[k], as_[k], gs[k])
+        assert np.array_equal(o.navi_map, nv[k]), k
+        ora.append(o)
+    dist = env.heuristic_distances().cpu().numpy()
+    for k in range(B):
+        assert np.array_equal(ora[k].dist_map, dist[k]), k
+    obs, pos = env.observe()
+    obs = obs.cpu().numpy()
+    for k in range(B):
+        assert np.array_equal(ora[k].observe()[0].astype(np.uint8), obs[k])
+    for s in range(T):
+        mode = s % 4
+        if mode == 0:
+            acts = rng.integers(0, 5, size=(B, N))
+        elif mode == 1:
+            acts = np.broadcast_to(rng.integers(1, 5, size=(B, 1)), (B, N))
+        elif mode == 2:
+            acts = greedy_actions(obs, rng, eps=0.2)
+        else:
+            acts = rng.integers(1, 5, size=(B, N))
+        acts = np.ascontiguousarray(acts, dtype=np.uint8)
+        if s == T - 1:
+            acts[:] = 0
+        g_obs, g_rew, g_done = env.step(acts)
+        obs, g_rew, g_done = g_obs.cpu().numpy(), g_rew.cpu().numpy(), g_done.cpu().numpy()
+        g_pos = env.agents_pos.cpu().numpy()
+        for k in range(B):
+            (o_obs, o_pos), o_rew, o_done, info = ora[k].step(acts[k])
+            assert np.array_equal(o_pos, g_pos[k]), (k, s)
+            assert np.array_equal(np.asarray(o_rew, dtype=np.float32), g_rew[k]), (k, s)
+            assert int(o_done) == g_done[k], (k, s)
+            assert np.array_equal(o_obs.astype(np.uint8), obs[k]), (k, s)
+    env.check()
+
+
+def test_observe_corners_and_borders():
+    L, N = 9, 6
+    m = np.zeros((L, L), dtype=np.uint8)
+    m[4, 4] = 1
+    a = np.array([[0, 0], [0, L - 1], [L - 1, 0], [L - 1, L - 1], [0, 1], [4, 0]], dtype=np.uint8)
+    g = np.array([[8, 8], [8, 0], [0, 8], [0, 0], [5, 5], [4, 8]], dtype=np.uint8)
+    env = make_env(1, N, L)
+    env.load(m[None], a[None], g[None])
+    obs, pos = env.observe()
+    obs = obs[0].cpu().numpy()
+    o = oracle.OracleEnv()
+    o.load(m, a, g)
+    assert np.array_equal(o.observe()[0].astype(np.uint8), obs)
+    assert obs[0, 1].sum() == 1 and obs[0, 1, 8, 8] == 1      # the obstacle at (4,4) seen from (0,0); outside = 0
+    assert obs[0, 0, 4, 5] == 1 and obs[0, 0, 4, 4] == 0      # neighbour visible, own centre cleared
+    assert obs[0, :, :4, :].sum() == 0 and obs[0, :, :, :4].sum() == 0   # everything outside the map is 0
+
+
+def test_invalid_action_latches_assertion():
+    m, a, g = random_instance(np.random.default_rng(0), 8, 4, 0.1)
+    env = make_env(1, 4, 8)
+    env.load(m[None], a[None], g[None])
+    env.step(np.array([[0, 7, 1, 2]], dtype=np.uint8))
+    with pytest.raises(AssertionError):
+        env.check()
+    env.check()  # cleared
+
+
+def test_subset_reload_and_obs_into_replay_slot():
+    import torch
+    maps, agents, goals = instances(32)
+    env = make_env(8, 32, 40)
+    env.load(maps[:8], agents[:8], goals[:8])
+    acts = np.random.default_rng(0).integers(0, 5, size=(8, 32)).astype(np.uint8)
+    replay = torch.zeros((3, 8, 32, 6, 9, 9), dtype=torch.uint8, device=env.device)
+    env.step(acts, out_obs=replay[1])
+    env.load(maps[100:102], agents[100:102], goals[100:102], env_ids=[5, 2])
+    assert np.array_equal(env.steps.cpu().numpy(), [1, 1, 0, 1, 1, 0, 1, 1])
+    obs, pos = env.observe()
+    o = oracle.OracleEnv()
+    o.load(maps[101], agents[101], goals[101])
+    assert np.array_equal(o.observe()[0].astype(np.uint8), obs[2].cpu().numpy())
+    o.load(maps[3], agents[3], goals[3])
+    (oo, _), _, _, _ = o.step(acts[3])
+    assert np.array_equal(oo.astype(np.uint8), replay[1, 3].cpu().numpy())
+    assert replay[0].sum() == 0 and replay[2].sum() == 0
+
+
+def test_step_host_entry_point():
+    maps, agents, goals = instances(16)
+    env = make_env(4, 16, 40)
+    env.load(maps[:4], agents[:4], goals[:4])
+    acts = np.random.default_rng(1).integers(0, 5, size=(4, 16)).astype(np.uint8)
+    obs, rew, done, steps = env.step_host(acts, want_obs=True)
+    for k in range(4):
+        o = oracle.OracleEnv()
+        o.load(maps[k], agents[k], goals[k])
+        (oo, op), orw, od, _ = o.step(acts[k])
+        assert np.array_equal(oo.astype(np.uint8), obs[k])
+        assert np.array_equal(np.asarray(orw, dtype=np.float32), rew[k])
+        assert int(od) == done[k] and steps[k] == 1
