@@ -1,0 +1,538 @@
+// mapf_step_kernels.cu — K1 + K2: Environment.step (environment.py:278-430) fused with the observe()
+// it ends in (environment.py:430, 433-467), hand-written for sm_100a.
+//
+// One warp per environment, lane = agent (K = ceil(N/32) agents per lane).  Per environment:
+//   1. all inputs of the env (positions, goals, actions, step counter, obstacle bitmap) are requested
+//      up front so their DRAM/L2 latencies overlap;
+//   2. conflict resolution runs in registers / shared memory (order-independent fixed point of the
+//      reference's restart-on-change scans);
+//   3. every lane gathers its agent's 6 x 9 x 9 window as a 486-BIT stream (obstacle / agent bitmaps in
+//      shared memory, heuristic bits straight from the nibble-planar navi array) and streams it, word
+//      by word, into the env's dense bit stream in shared memory;
+//   4. the warp expands bits to bool bytes and writes the env's N*486-byte block with fully coalesced
+//      128-bit stores.
+// HBM-bound (486 B written per agent-step); nothing here is a dense contraction, so no tensor cores.
+#include <cstdlib>
+#include <type_traits>
+
+#include "mapf_common.cuh"
+
+namespace {
+
+struct StepParams {
+    EnvDims d;
+    const uint32_t *obst;
+    uint8_t *pos;
+    const uint8_t *goal;
+    const uint32_t *navi;
+    int32_t *steps;
+    int32_t *err;
+    const uint8_t *actions;  // [B,N]           (step only)
+    uint8_t *obs;            // [B,N,6,9,9]
+    float *rewards;          // [B,N]           (step only)
+    uint8_t *done;           // [B]             (step only)
+    int32_t *steps_out;      // [B] optional
+    uint8_t *pos_out;        // [B,N,2] optional (observe only)
+    float r_move, r_stay_on, r_stay_off, r_collision, r_finish;
+    int warp_smem_words;     // per-warp shared memory, multiple of 4 words
+    int obst_words;          // = d.obst_stride
+    int bits_words;          // words of the per-env observation bit stream (also holds the occupancy grid)
+    int flags;               // MAPF_STEPF_*
+};
+
+enum : int {
+    MAPF_STEPF_NAVI_KEEP = 1,    // heuristic-map loads carry an L2 evict_last policy
+    MAPF_STEPF_OBS_POLICY = 2,   // observation stores carry an L2 evict_first policy (else st.global.cs)
+};
+
+// 4 bits -> 4 bool bytes: bit b lands at bit 8b.  The four shifted copies of x (shifts 0,7,14,21)
+// do not overlap for x < 16, so the multiply has no carries.
+__device__ __forceinline__ uint32_t expand4(uint32_t x) { return (x * 0x00204081u) & 0x01010101u; }
+
+__device__ __forceinline__ uint32_t window9(const uint32_t *row, int bitoff)
+{
+    const int w = bitoff >> 5;
+    return __funnelshift_r(row[w], row[w + 1], bitoff & 31) & 0x1ffu;
+}
+
+__device__ __forceinline__ uint64_t l2_policy_evict_last()
+{
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first()
+{
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ uint32_t ldg_policy(const uint32_t *ptr, uint64_t pol)
+{
+    uint32_t v;
+    asm("ld.global.nc.L2::cache_hint.b32 %0, [%1], %2;" : "=r"(v) : "l"(ptr), "l"(pol));
+    return v;
+}
+__device__ __forceinline__ void stg_policy(uint4 *ptr, const uint4 &v, uint64_t pol)
+{
+    asm volatile("st.global.L2::cache_hint.v4.b32 [%0], {%1, %2, %3, %4}, %5;"
+                 :
+                 : "l"(ptr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "l"(pol)
+                 : "memory");
+}
+
+// Compile-time walk over the 54 nine-bit fields (channel c = F / 9, window row u = F % 9) of one agent's
+// observation bit stream.  A 64-bit accumulator collects fields; every completed 32-bit word is handed to
+// `emit` immediately, so at most two stream words are live in registers at any time.
+template <int F>
+struct FieldWalk {
+    template <typename Val, typename Emit>
+    __device__ __forceinline__ static void run(uint64_t acc, Val &&val, Emit &&emit)
+    {
+        constexpr int pos = 9 * F, m = pos >> 5, s = pos & 31;
+        acc |= (uint64_t)val(std::integral_constant<int, F>{}) << s;
+        if constexpr (s + 9 >= 32) {
+            emit(std::integral_constant<int, m>{}, (uint32_t)acc);
+            acc >>= 32;
+        }
+        if constexpr (F + 1 < 54) FieldWalk<F + 1>::run(acc, val, emit);
+        else emit(std::integral_constant<int, 15>{}, (uint32_t)acc);  // bits 480..485
+    }
+};
+
+template <int RW, int K, bool DO_STEP, int WARPS, int MINB>
+__global__ void __launch_bounds__(WARPS * 32, MINB)
+step_observe_kernel(const StepParams p)
+{
+    constexpr int RWS = RW + 1;
+    extern __shared__ __align__(16) uint32_t smem[];
+    const EnvDims &d = p.d;
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int N = d.N, L = d.L;
+
+    uint32_t *s_obst = smem + (size_t)warp * p.warp_smem_words;
+    uint32_t *s_agent = s_obst + p.obst_words;
+    uint32_t *s_bits = s_agent + p.obst_words;
+    uint16_t *s_tgt = reinterpret_cast<uint16_t *>(s_bits + p.bits_words);
+    uint16_t *s_cell = s_tgt + 32 * K;
+    // The cell -> agent grid of the step phase lives in the bit-stream buffer (the two are never live at
+    // the same time).  It is never cleared: an entry is trusted only if it round-trips through s_cell.
+    uint8_t *s_occ = reinterpret_cast<uint8_t *>(s_bits);
+
+    const uint64_t pol_keep = l2_policy_evict_last();
+    const uint64_t pol_stream = l2_policy_evict_first();
+    const bool navi_keep = p.flags & MAPF_STEPF_NAVI_KEEP;
+    const bool obs_policy = p.flags & MAPF_STEPF_OBS_POLICY;
+
+    // the agent bitmap must start all-zero; afterwards each env clears the bits it set
+    for (int w = lane; w < p.obst_words; w += 32) s_agent[w] = 0;
+    __syncwarp();
+
+    for (int e = blockIdx.x * WARPS + warp; e < d.B; e += gridDim.x * WARPS) {
+        // ---- request every input of this env up front ----
+        int px[K], py[K];
+        bool valid[K];
+        [[maybe_unused]] int gx[K], gy[K], act[K];
+        [[maybe_unused]] int step_now = 0;
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            const int a = k * 32 + lane;
+            valid[k] = a < N;
+            px[k] = py[k] = 0;
+            if constexpr (DO_STEP) gx[k] = gy[k] = act[k] = 0;
+            if (valid[k]) {
+                const uchar2 pp = reinterpret_cast<const uchar2 *>(p.pos)[(size_t)e * N + a];
+                px[k] = pp.x;
+                py[k] = pp.y;
+                if constexpr (DO_STEP) {
+                    const uchar2 gg = __ldg(reinterpret_cast<const uchar2 *>(p.goal) + (size_t)e * N + a);
+                    gx[k] = gg.x;
+                    gy[k] = gg.y;
+                    act[k] = __ldg(p.actions + (size_t)e * N + a);
+                }
+            }
+        }
+        if constexpr (DO_STEP)
+            if (lane == 0) step_now = p.steps[e];
+        {
+            const uint4 *src = reinterpret_cast<const uint4 *>(p.obst + (size_t)e * d.obst_stride);
+            uint4 *dst = reinterpret_cast<uint4 *>(s_obst);
+            for (int w = lane; w < (p.obst_words >> 2); w += 32) dst[w] = __ldg(src + w);
+        }
+
+        if constexpr (DO_STEP) {
+            int tx[K], ty[K], tcell[K], mycell[K], occ_j[K];
+            float rew[K];
+            bool mover[K], occ_ok[K], fail[K];
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                const int a = k * 32 + lane;
+                if (act[k] > 4) {  // environment.py:289-290 raises; we latch and treat as stay
+                    atomicOr(p.err, MAPF_ERRBIT_ACTION);
+                    act[k] = 0;
+                }
+                mycell[k] = px[k] * L + py[k];
+                s_cell[a] = valid[k] ? (uint16_t)mycell[k] : (uint16_t)0xffff;
+                if (valid[k]) s_occ[mycell[k]] = (uint8_t)a;
+            }
+            __syncwarp();  // staged obstacle bitmap, s_cell and s_occ visible to every lane
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                // stay / move pass, environment.py:298-311
+                const bool on_goal = px[k] == gx[k] && py[k] == gy[k];
+                rew[k] = act[k] == 0 ? (on_goal ? p.r_stay_on : p.r_stay_off) : p.r_move;
+                mover[k] = valid[k] && act[k] != 0;
+                // action table environment.py:12
+                tx[k] = px[k] + (act[k] == 2) - (act[k] == 1);
+                ty[k] = py[k] + (act[k] == 4) - (act[k] == 3);
+                tcell[k] = tx[k] * L + ty[k];
+                if (mover[k]) {
+                    // round 1: out of range / obstacle, environment.py:320-332
+                    bool bad = tx[k] < 0 || ty[k] < 0 || tx[k] >= L || ty[k] >= L;
+                    if (!bad) bad = (s_obst[(tx[k] + 4) * RWS + ((ty[k] + 4) >> 5)] >> ((ty[k] + 4) & 31)) & 1u;
+                    if (bad) {
+                        rew[k] = p.r_collision;
+                        mover[k] = false;
+                    }
+                }
+                s_tgt[k * 32 + lane] = mover[k] ? (uint16_t)tcell[k] : (uint16_t)0xffff;
+            }
+            __syncwarp();
+            // round 2: swap, environment.py:335-365 (order-independent form: both partners revert)
+            bool swapped[K];
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                occ_j[k] = 0xff;
+                occ_ok[k] = false;
+                swapped[k] = false;
+                if (mover[k]) {
+                    const int j = s_occ[tcell[k]];
+                    occ_ok[k] = j < N && s_cell[j] == (uint16_t)tcell[k];
+                    occ_j[k] = j;
+                    swapped[k] = occ_ok[k] && s_tgt[j] == (uint16_t)mycell[k];
+                }
+            }
+            __syncwarp();
+#pragma unroll
+            for (int k = 0; k < K; ++k)
+                if (swapped[k]) {
+                    s_tgt[k * 32 + lane] = 0xffff;
+                    mover[k] = false;
+                    rew[k] = p.r_collision;
+                }
+            __syncwarp();
+            // round 3: vertex conflicts, environment.py:369-406, as the greatest fixed point:
+            //   fail if the target's occupant is not a live mover,
+            //   fail if not the lowest id among live movers with the same target (:389-394),
+            //   fail if the target's occupant is a live mover that fails (propagates backwards).
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                fail[k] = mover[k] && occ_ok[k] && s_tgt[occ_j[k]] == 0xffff;
+                bool lower_claim = false;
+                if (K > 1 && k > 0 && mover[k]) {
+                    const int c = s_occ[tcell[k]];  // claim left by a lower slot (verified, never cleared)
+                    lower_claim = c < N && (c >> 5) < k && s_tgt[c] == (uint16_t)tcell[k];
+                }
+                const unsigned code = mover[k] ? (unsigned)tcell[k] : (0x10000u | lane);
+                const unsigned m = __match_any_sync(MAPF_FULL_MASK, code);
+                const bool first = (__ffs(m) - 1) == lane;
+                if (mover[k] && (!first || lower_claim)) fail[k] = true;
+                if (K > 1 && k + 1 < K) {
+                    __syncwarp();
+                    if (mover[k]) s_occ[tcell[k]] = (uint8_t)(k * 32 + lane);
+                    __syncwarp();
+                }
+            }
+            for (;;) {
+                unsigned fm[K];
+#pragma unroll
+                for (int k = 0; k < K; ++k) fm[k] = __ballot_sync(MAPF_FULL_MASK, fail[k]);
+                bool changed = false;
+#pragma unroll
+                for (int k = 0; k < K; ++k) {
+                    if (mover[k] && !fail[k] && occ_ok[k]) {
+                        const int j = occ_j[k];
+                        unsigned mj = fm[0];
+#pragma unroll
+                        for (int q = 1; q < K; ++q)
+                            if ((j >> 5) == q) mj = fm[q];
+                        if ((mj >> (j & 31)) & 1u) {
+                            fail[k] = true;
+                            changed = true;
+                        }
+                    }
+                }
+                if (!__any_sync(MAPF_FULL_MASK, changed)) break;
+            }
+            // commit, environment.py:410-421
+            bool all_goal = true;
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                if (mover[k]) {
+                    if (fail[k]) rew[k] = p.r_collision;
+                    else {
+                        px[k] = tx[k];
+                        py[k] = ty[k];
+                    }
+                }
+                all_goal = all_goal && (!valid[k] || (px[k] == gx[k] && py[k] == gy[k]));
+            }
+            const bool done = __all_sync(MAPF_FULL_MASK, all_goal);
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                const int a = k * 32 + lane;
+                if (valid[k]) {
+                    reinterpret_cast<uchar2 *>(p.pos)[(size_t)e * N + a] = make_uchar2((unsigned char)px[k], (unsigned char)py[k]);
+                    p.rewards[(size_t)e * N + a] = done ? p.r_finish : rew[k];
+                }
+            }
+            if (lane == 0) {
+                const int st = step_now + 1;
+                p.steps[e] = st;
+                if (p.steps_out) p.steps_out[e] = st;
+                p.done[e] = done ? 1 : 0;
+            }
+        } else {
+            if (p.pos_out) {
+#pragma unroll
+                for (int k = 0; k < K; ++k)
+                    if (valid[k])
+                        reinterpret_cast<uchar2 *>(p.pos_out)[(size_t)e * N + k * 32 + lane] =
+                            make_uchar2((unsigned char)px[k], (unsigned char)py[k]);
+            }
+            __syncwarp();  // s_obst visible
+        }
+
+        // ---------------- observe, environment.py:433-467 ----------------
+        // agent bitmap (environment.py:449-451): one shared-memory atomic per agent
+#pragma unroll
+        for (int k = 0; k < K; ++k)
+            if (valid[k]) atomicOr(&s_agent[(px[k] + 4) * RWS + ((py[k] + 4) >> 5)], 1u << ((py[k] + 4) & 31));
+        __syncwarp();  // also orders the last s_occ reads before the bit stream overwrites that buffer
+
+        const size_t env_bytes = (size_t)N * MAPF_OBS_BYTES_PER_AGENT;
+        uint8_t *obs_env = p.obs + (size_t)e * env_bytes;
+        const int head = (int)(reinterpret_cast<uintptr_t>(obs_env) & 15);  // bytes before the 16-B boundary
+
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            const int a = k * 32 + lane;
+            // this agent's 486 bits start at stream bit (head + 486 a) = word f, bit o
+            const int gbit = head + MAPF_OBS_BYTES_PER_AGENT * a;
+            const int o = gbit & 31;
+            uint32_t *S = s_bits + (gbit >> 5);
+            uint32_t x0 = 0;
+            if (valid[k]) {
+                const int x = px[k], y = py[k];
+                // window rows x-4..x+4 are padded rows x..x+8; columns y-4..y+4 are padded bits y..y+8
+                const uint32_t *nb = p.navi + ((size_t)e * N + a) * d.navi_agent_stride + (size_t)(y >> 3) * d.R + x;
+                uint32_t wa[9], wb[9];
+                if (navi_keep) {
+#pragma unroll
+                    for (int u = 0; u < 9; ++u) {
+                        wa[u] = ldg_policy(nb + u, pol_keep);
+                        wb[u] = ldg_policy(nb + d.R + u, pol_keep);
+                    }
+                } else {
+#pragma unroll
+                    for (int u = 0; u < 9; ++u) {
+                        wa[u] = __ldg(nb + u);
+                        wb[u] = __ldg(nb + d.R + u);
+                    }
+                }
+                const int sh = y & 7;
+                const uint32_t *ag_row = s_agent + x * RWS, *ob_row = s_obst + x * RWS;
+                uint32_t prev = 0;
+                auto val = [&](auto fc) -> uint32_t {
+                    constexpr int f = decltype(fc)::value, c = f / 9, u = f % 9;
+                    if constexpr (c == 0) {
+                        uint32_t v = window9(ag_row + u * RWS, y);
+                        if constexpr (u == 4) v &= ~0x10u;  // own centre cleared, environment.py:461
+                        return v;
+                    } else if constexpr (c == 1) {
+                        return window9(ob_row + u * RWS, y);
+                    } else {
+                        // byte c-2 of wa / wb = direction c-2 bits of columns 8cb.. / 8cb+8..
+                        constexpr uint32_t sel = 0x0040u + 0x11u * (c - 2);
+                        return (__byte_perm(wa[u], wb[u], sel) >> sh) & 0x1ffu;
+                    }
+                };
+                auto emit = [&](auto mc, uint32_t w) {
+                    constexpr int m = decltype(mc)::value;
+                    if constexpr (m == 0) x0 = w << o;
+                    else S[m] = __funnelshift_l(prev, w, o);
+                    prev = w;
+                };
+                FieldWalk<0>::run(0ull, val, emit);
+                if (((o + 485) >> 5) == 16) S[16] = __funnelshift_l(prev, 0u, o);
+            }
+            __syncwarp();
+            // first word: shared with the previous agent's last word unless this agent starts a word
+            if (valid[k]) {
+                if (o == 0 || a == 0) S[0] = x0;
+                else S[0] |= x0;
+            }
+            __syncwarp();
+        }
+
+        // expand 1 bit -> 1 bool byte, 16 bytes per lane per store, fully coalesced streaming stores
+        {
+            const int total = head + (int)env_bytes;
+            const int c_lo = (head + 15) >> 4, c_hi = total >> 4;  // chunks [c_lo, c_hi) are whole
+            uint8_t *obase = obs_env - head;                       // 16-byte aligned
+            const uint16_t *S16 = reinterpret_cast<const uint16_t *>(s_bits);
+#pragma unroll 4
+            for (int c = c_lo + lane; c < c_hi; c += 32) {
+                const uint32_t s = S16[c];
+                uint4 v;
+                v.x = expand4(s & 0xfu);
+                v.y = expand4((s >> 4) & 0xfu);
+                v.z = expand4((s >> 8) & 0xfu);
+                v.w = expand4(s >> 12);
+                uint4 *dst = reinterpret_cast<uint4 *>(obase + (c << 4));
+                if (obs_policy) stg_policy(dst, v, pol_stream);
+                else __stcs(dst, v);
+            }
+            // ragged first / last chunk of an unaligned observation block
+            if ((head != 0 && lane == 0) || ((total & 15) != 0 && lane == 1)) {
+                const int c = lane == 0 ? 0 : c_hi;
+                const uint32_t s = S16[c];
+                for (int b = 0; b < 16; ++b) {
+                    const int g = (c << 4) + b;
+                    if (g >= head && g < total) obase[g] = (uint8_t)((s >> b) & 1u);
+                }
+            }
+        }
+        __syncwarp();
+        // clear the agent bits this env set
+#pragma unroll
+        for (int k = 0; k < K; ++k)
+            if (valid[k]) s_agent[(px[k] + 4) * RWS + ((py[k] + 4) >> 5)] = 0;
+        __syncwarp();
+    }
+}
+
+// ---- launch plumbing ---------------------------------------------------------------------------
+struct StepTuning {
+    int variant;  // CTA shape / register cap of the (RW = 2, K = 1) instantiation, see launch_step_rwk
+    int flags;
+};
+
+const StepTuning &tuning()
+{
+    static const StepTuning t = [] {
+        StepTuning r{1, MAPF_STEPF_NAVI_KEEP};
+        if (const char *s = std::getenv("MAPF_STEP_VARIANT")) r.variant = std::atoi(s);
+        if (const char *s = std::getenv("MAPF_STEP_FLAGS")) r.flags = std::atoi(s);
+        return r;
+    }();
+    return t;
+}
+
+template <int RW, int K, bool DO_STEP, int WARPS, int MINB>
+int launch_step_cfg(const mapf_env *env, StepParams &p, cudaStream_t st)
+{
+    auto kern = step_observe_kernel<RW, K, DO_STEP, WARPS, MINB>;
+    const size_t smem = (size_t)p.warp_smem_words * 4 * WARPS;
+    if (smem > 227 * 1024) {
+        mapf_set_error("map too large for the step kernel's shared memory");
+        return MAPF_EINVAL;
+    }
+    if (smem > 48 * 1024)  // per-device attribute; cheap enough to set on every large-smem launch
+        MAPF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int grid = (env->d.B + WARPS - 1) / WARPS;
+    kern<<<grid, WARPS * 32, smem, st>>>(p);
+    MAPF_CUDA(cudaGetLastError());
+    return MAPF_OK;
+}
+
+template <int RW, int K, bool DO_STEP>
+int launch_step_rwk(const mapf_env *env, StepParams &p, cudaStream_t st)
+{
+    if constexpr (RW == 2 && K == 1 && DO_STEP) {
+        switch (tuning().variant) {
+            case 0: return launch_step_cfg<RW, K, DO_STEP, 8, 5>(env, p, st);
+            case 2: return launch_step_cfg<RW, K, DO_STEP, 4, 16>(env, p, st);
+            case 3: return launch_step_cfg<RW, K, DO_STEP, 2, 32>(env, p, st);
+            default: break;
+        }
+    }
+    return launch_step_cfg<RW, K, DO_STEP, 4, (K == 1 ? 12 : 1)>(env, p, st);
+}
+
+template <int RW, bool DO_STEP>
+int launch_step_rw(const mapf_env *env, StepParams &p, cudaStream_t st)
+{
+    switch (env->d.K) {
+        case 1: return launch_step_rwk<RW, 1, DO_STEP>(env, p, st);
+        case 2: return launch_step_rwk<RW, 2, DO_STEP>(env, p, st);
+        case 3: return launch_step_rwk<RW, 3, DO_STEP>(env, p, st);
+        case 4: return launch_step_rwk<RW, 4, DO_STEP>(env, p, st);
+    }
+    mapf_set_error("unsupported agent count");
+    return MAPF_EINVAL;
+}
+
+template <bool DO_STEP>
+int launch_step(const mapf_env *env, StepParams &p, cudaStream_t st)
+{
+    switch (env->d.RW) {
+        case 1: return launch_step_rw<1, DO_STEP>(env, p, st);
+        case 2: return launch_step_rw<2, DO_STEP>(env, p, st);
+        case 3: return launch_step_rw<3, DO_STEP>(env, p, st);
+        case 4: return launch_step_rw<4, DO_STEP>(env, p, st);
+    }
+    mapf_set_error("unsupported map size");
+    return MAPF_EINVAL;
+}
+
+StepParams make_params(const mapf_env *env)
+{
+    StepParams p{};
+    const EnvDims &d = env->d;
+    p.d = d;
+    p.obst = env->obst;
+    p.pos = env->pos;
+    p.goal = env->goal;
+    p.navi = env->navi;
+    p.steps = env->steps;
+    p.err = env->err;
+    p.r_move = env->reward[0];
+    p.r_stay_on = env->reward[1];
+    p.r_stay_off = env->reward[2];
+    p.r_collision = env->reward[3];
+    p.r_finish = env->reward[4];
+    p.obst_words = d.obst_stride;
+    // stream words: 15 head bits max + N*486 bits, +2 words of slack for the u16 tail read; the same
+    // buffer holds the L*L-byte occupancy grid of the step phase
+    const int stream_words = ((15 + d.N * MAPF_OBS_BYTES_PER_AGENT + 31) >> 5) + 2;
+    const int occ_words = (d.L * d.L + 3) >> 2;
+    p.bits_words = stream_words > occ_words ? stream_words : occ_words;
+    const int words = 2 * p.obst_words + p.bits_words + (32 * d.K) /* s_tgt + s_cell, u16 each */;
+    p.warp_smem_words = (words + 3) & ~3;
+    p.flags = tuning().flags;
+    return p;
+}
+
+}  // namespace
+
+int mapf_launch_step(mapf_env *env, const uint8_t *d_actions, uint8_t *d_obs, float *d_rewards, uint8_t *d_done,
+                     int32_t *d_steps, cudaStream_t st)
+{
+    StepParams p = make_params(env);
+    p.actions = d_actions;
+    p.obs = d_obs;
+    p.rewards = d_rewards;
+    p.done = d_done;
+    p.steps_out = d_steps;
+    return launch_step<true>(env, p, st);
+}
+
+int mapf_launch_observe(mapf_env *env, uint8_t *d_obs, uint8_t *d_pos, cudaStream_t st)
+{
+    StepParams p = make_params(env);
+    p.obs = d_obs;
+    p.pos_out = d_pos;
+    return launch_step<false>(env, p, st);
+}
