@@ -41,6 +41,7 @@ extern "C" {
 #define MAPF_EACTION (-3)  /* an action was outside 0..4 (environment.py:289-290)    */
 #define MAPF_EUNIQUE (-4)  /* two agents share a cell (environment.py:424-428)       */
 #define MAPF_ENOMEM (-5)
+#define MAPF_ENOSPACE (-6) /* reset could not place the agents ('no empty position', environment.py:31) */
 
 #define MAPF_OBS_RADIUS 4  /* config.py:14 — the only radius any reference consumer uses */
 #define MAPF_FOV 9
@@ -117,7 +118,7 @@ int mapf_env_get_state(mapf_env *env, uint8_t *d_map, uint8_t *d_pos, uint8_t *d
 /* Overwrite agent positions / step counters (used to restore snapshots). Either may be NULL. */
 int mapf_env_set_state(mapf_env *env, const uint8_t *d_pos, const int32_t *d_steps, void *stream);
 
-/* Synchronous: returns the latched error (MAPF_OK, MAPF_EACTION, MAPF_EUNIQUE) and clears it. */
+/* Synchronous: returns the latched error (MAPF_OK, MAPF_EACTION, MAPF_EUNIQUE, MAPF_ENOSPACE) and clears it. */
 int mapf_env_status(mapf_env *env, void *stream);
 
 /* ---- Environment.reset instance generation (environment.py:146-196), device side ----------- */

@@ -9,7 +9,7 @@ from . import build as _build
 
 _lib = None
 
-MAPF_OK, MAPF_EINVAL, MAPF_ECUDA, MAPF_EACTION, MAPF_EUNIQUE, MAPF_ENOMEM = 0, -1, -2, -3, -4, -5
+MAPF_OK, MAPF_EINVAL, MAPF_ECUDA, MAPF_EACTION, MAPF_EUNIQUE, MAPF_ENOMEM, MAPF_ENOSPACE = 0, -1, -2, -3, -4, -5, -6
 
 
 class EnvConfig(C.Structure):
@@ -80,4 +80,6 @@ def check(code: int):
         msg = lib().mapf_last_error().decode("utf-8", "replace")
         if code == MAPF_EACTION:
             raise AssertionError("action index out of range")  # environment.py:290
+        if code in (MAPF_EUNIQUE, MAPF_ENOSPACE):
+            raise RuntimeError(msg)  # 'unique' (environment.py:428) / 'no empty position' (environment.py:31)
         raise MapfError(code, msg)

@@ -2,6 +2,7 @@
 // Argument validation, arena ownership and stream plumbing only; the kernels live in
 // mapf_env_kernels.cu / mapf_reset_kernels.cu / mapf_per_kernels.cu.
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 
@@ -112,10 +113,10 @@ int mapf_env_create(const mapf_env_config *cfg, mapf_env **out)
     d.R = d.L + 8;
     d.RW = (d.L + 8 + 31) / 32;
     d.RWS = d.RW + 1;
-    d.CB = (d.L + 8 + 7) / 8;
+    d.NB = (d.L + 7) / 8;
     d.K = (d.N + 31) / 32;
     d.obst_stride = (d.R * d.RWS + 3) & ~3;
-    d.navi_agent_stride = d.CB * d.R;
+    d.navi_agent_stride = d.NB * d.NB * 32;
     env->device = cfg->device;
     for (int i = 0; i < 5; ++i) env->reward[i] = cfg->reward_fn[i];
 
@@ -315,6 +316,10 @@ int mapf_env_status(mapf_env *env, void *stream)
     if (bits & MAPF_ERRBIT_UNIQUE) {
         mapf_set_error("unique");
         return MAPF_EUNIQUE;
+    }
+    if (bits & MAPF_ERRBIT_RESET) {
+        mapf_set_error("no empty position");  // environment.py:31
+        return MAPF_ENOSPACE;
     }
     return MAPF_OK;
 }

@@ -9,10 +9,14 @@
 //                                   two-word funnel shift with no bounds checks (outside the map = 0,
 //                                   environment.py:447).
 //   pos    u8[B][N][2], goal u8[B][N][2]   (x, y) = (row, col)
-//   navi   u32[B][N][CB][R]         heuristic bits (environment.py:253-276).  Word [cb][r] holds, for padded
-//                                   row r and the 8 padded columns 8*cb .. 8*cb+7, one byte per direction
-//                                   d = 0 up, 1 down, 2 left, 3 right (byte d, bit c = column 8*cb + c).
-//                                   A 9x9 window therefore reads two runs of 9 consecutive words.
+//   navi   u64[B][N][NB][NB][16]    heuristic bits (environment.py:253-276) as OVERLAPPING 16x16-cell tiles of
+//                                   the padded grid, one 128-byte line each: tile (bx, by) covers padded rows
+//                                   8bx .. 8bx+15 and padded columns 8by .. 8by+15; its row r is one u64 whose
+//                                   bit 16 d + c is direction d (0 up, 1 down, 2 left, 3 right) at column
+//                                   8by + c.  The 9x9 window of an agent at (x, y) (padded top-left corner
+//                                   (x, y)) lies entirely inside tile (x >> 3, y >> 3): 9 consecutive u64 of
+//                                   ONE aligned 128-byte line, whatever the position (every cell is stored in
+//                                   up to 4 tiles; NB = ceil(L / 8) tiles per side).
 //   steps  i32[B]
 #pragma once
 #include <cuda_runtime.h>
@@ -29,10 +33,10 @@ struct EnvDims {
     int R;            // L + 8 padded rows
     int RW;           // words holding the L + 8 padded column bits
     int RWS;          // RW + 1: row stride in words
-    int CB;           // ceil((L + 8) / 8) column blocks
+    int NB;           // ceil(L / 8): navi tiles per side
     int K;            // ceil(N / 32) agent slots per lane
     int obst_stride;  // words per env in `obst` (R * RWS rounded up to 4)
-    int navi_agent_stride;  // CB * R words per agent
+    int navi_agent_stride;  // NB * NB * 32 words (NB * NB tiles of 128 bytes) per agent
 };
 
 struct mapf_env {
@@ -83,3 +87,4 @@ int mapf_cuda_fail(cudaError_t e, const char *what);
 
 #define MAPF_ERRBIT_ACTION 1
 #define MAPF_ERRBIT_UNIQUE 2
+#define MAPF_ERRBIT_RESET 4

@@ -58,14 +58,16 @@ __global__ void pack_load_kernel(EnvDims d, const int32_t *__restrict__ env_ids,
 // ---------------------------------------------------------------------------------------------
 template <int RW, int RPL>
 __global__ void __launch_bounds__(kBfsWarps * 32)
-bfs_navi_kernel(EnvDims d, const int32_t *__restrict__ env_ids, int n, const uint32_t *__restrict__ obst,
-                const uint8_t *__restrict__ goal, uint32_t *__restrict__ navi, int32_t *__restrict__ dist_out)
+bfs_navi_kernel(EnvDims d, const int32_t *__restrict__ env_ids, const uint8_t *__restrict__ env_mask, int n,
+                const uint32_t *__restrict__ obst, const uint8_t *__restrict__ goal, uint32_t *__restrict__ navi,
+                int32_t *__restrict__ dist_out)
 {
     const int lane = lane_id();
     const int g = blockIdx.x * kBfsWarps + (threadIdx.x >> 5);
     if (g >= n * d.N) return;
     const int i = g / d.N, a = g - i * d.N;
     const int e = env_ids ? env_ids[i] : i;
+    if (env_mask && !env_mask[e]) return;  // masked re-computation after a device-side reset
     const uint32_t *ob = obst + (size_t)e * d.obst_stride;
 
     uint32_t fre[RPL][RW], vis[RPL][RW], fro[RPL][RW], pl[4][RPL][RW];
@@ -155,22 +157,28 @@ bfs_navi_kernel(EnvDims d, const int32_t *__restrict__ env_ids, int n, const uin
             }
     }
 
-    // emit [cb][row] words: byte k = 8 column bits of direction k
-    uint32_t *nv = navi + ((size_t)e * d.N + a) * d.navi_agent_stride;
+    // emit the overlapping 16x16 tiles (mapf_common.cuh): this lane owns padded row pr = row + 4, which is
+    // row pr & 7 of tile row-block pr >> 3 and row (pr & 7) + 8 of the block above
+    uint2 *nv = reinterpret_cast<uint2 *>(navi + ((size_t)e * d.N + a) * d.navi_agent_stride);
 #pragma unroll
     for (int q = 0; q < RPL; ++q) {
-        int row = lane + 32 * q;
+        const int row = lane + 32 * q;
+        if (row >= d.L) continue;
+        const int pr = row + 4, bx1 = pr >> 3, r1 = pr & 7;
 #pragma unroll
-        for (int w = 0; w < RW; ++w)
+        for (int by = 0; by < 4 * RW; ++by) {
+            if (by >= d.NB) continue;
+            constexpr int kLast = RW - 1;
+            const int w = by >> 2;          // compile-time after unrolling
+            const int s = (by & 3) * 8;
+            uint32_t f[4];
 #pragma unroll
-            for (int b = 0; b < 4; ++b) {
-                int cb = 4 * w + b;
-                if (cb < d.CB && row < d.L) {
-                    uint32_t v = ((pl[0][q][w] >> (8 * b)) & 0xffu) | (((pl[1][q][w] >> (8 * b)) & 0xffu) << 8) |
-                                 (((pl[2][q][w] >> (8 * b)) & 0xffu) << 16) | (((pl[3][q][w] >> (8 * b)) & 0xffu) << 24);
-                    nv[cb * d.R + row + 4] = v;
-                }
-            }
+            for (int k = 0; k < 4; ++k)
+                f[k] = __funnelshift_r(pl[k][q][w], w < kLast ? pl[k][q][w < kLast ? w + 1 : kLast] : 0u, s) & 0xffffu;
+            const uint2 v = make_uint2(f[0] | (f[1] << 16), f[2] | (f[3] << 16));
+            if (bx1 < d.NB) nv[((size_t)(bx1 * d.NB + by) << 4) + r1] = v;
+            if (bx1 > 0) nv[((size_t)((bx1 - 1) * d.NB + by) << 4) + r1 + 8] = v;
+        }
     }
 }
 
@@ -198,8 +206,11 @@ __global__ void unpack_navi_kernel(EnvDims d, const uint32_t *__restrict__ navi,
     int x = (idx / d.L) % d.L;
     int k = (idx / ((size_t)d.L * d.L)) % 4;
     size_t ea = idx / ((size_t)4 * d.L * d.L);
-    uint32_t w = navi[ea * d.navi_agent_stride + (size_t)((y + 4) >> 3) * d.R + x + 4];
-    navi_out[idx] = (w >> (8 * k + ((y + 4) & 7))) & 1u;
+    const int pr = x + 4, pc = y + 4;
+    const int bx = min(pr >> 3, d.NB - 1), by = min(pc >> 3, d.NB - 1);
+    const uint2 v = reinterpret_cast<const uint2 *>(navi + ea * d.navi_agent_stride)[((size_t)(bx * d.NB + by) << 4) + (pr - 8 * bx)];
+    const uint32_t half = k < 2 ? v.x : v.y;
+    navi_out[idx] = (half >> (16 * (k & 1) + (pc - 8 * by))) & 1u;
 }
 
 }  // namespace
@@ -215,33 +226,45 @@ int mapf_launch_pack_load(mapf_env *env, const int32_t *d_env_ids, int n, const 
 }
 
 template <int RW>
-static int launch_bfs_rw(mapf_env *env, const int32_t *ids, int n, int32_t *dist, cudaStream_t st)
+static int launch_bfs_rw(mapf_env *env, const int32_t *ids, const uint8_t *mask, int n, int32_t *dist, cudaStream_t st)
 {
     const EnvDims &d = env->d;
     const int rpl = (d.L + 31) / 32;
     const long warps = (long)n * d.N;
     const int grid = (int)((warps + kBfsWarps - 1) / kBfsWarps);
     switch (rpl) {
-        case 1: bfs_navi_kernel<RW, 1><<<grid, kBfsWarps * 32, 0, st>>>(d, ids, n, env->obst, env->goal, env->navi, dist); break;
-        case 2: bfs_navi_kernel<RW, 2><<<grid, kBfsWarps * 32, 0, st>>>(d, ids, n, env->obst, env->goal, env->navi, dist); break;
-        case 3: bfs_navi_kernel<RW, 3><<<grid, kBfsWarps * 32, 0, st>>>(d, ids, n, env->obst, env->goal, env->navi, dist); break;
-        case 4: bfs_navi_kernel<RW, 4><<<grid, kBfsWarps * 32, 0, st>>>(d, ids, n, env->obst, env->goal, env->navi, dist); break;
+        case 1: bfs_navi_kernel<RW, 1><<<grid, kBfsWarps * 32, 0, st>>>(d, ids, mask, n, env->obst, env->goal, env->navi, dist); break;
+        case 2: bfs_navi_kernel<RW, 2><<<grid, kBfsWarps * 32, 0, st>>>(d, ids, mask, n, env->obst, env->goal, env->navi, dist); break;
+        case 3: bfs_navi_kernel<RW, 3><<<grid, kBfsWarps * 32, 0, st>>>(d, ids, mask, n, env->obst, env->goal, env->navi, dist); break;
+        case 4: bfs_navi_kernel<RW, 4><<<grid, kBfsWarps * 32, 0, st>>>(d, ids, mask, n, env->obst, env->goal, env->navi, dist); break;
         default: mapf_set_error("unsupported map size"); return MAPF_EINVAL;
     }
     MAPF_CUDA(cudaGetLastError());
     return MAPF_OK;
 }
 
-int mapf_launch_bfs(mapf_env *env, const int32_t *d_env_ids, int n, int32_t *d_dist_out, cudaStream_t st)
+static int launch_bfs(mapf_env *env, const int32_t *d_env_ids, const uint8_t *d_mask, int n, int32_t *d_dist_out,
+                      cudaStream_t st)
 {
     switch (env->d.RW) {
-        case 1: return launch_bfs_rw<1>(env, d_env_ids, n, d_dist_out, st);
-        case 2: return launch_bfs_rw<2>(env, d_env_ids, n, d_dist_out, st);
-        case 3: return launch_bfs_rw<3>(env, d_env_ids, n, d_dist_out, st);
-        case 4: return launch_bfs_rw<4>(env, d_env_ids, n, d_dist_out, st);
+        case 1: return launch_bfs_rw<1>(env, d_env_ids, d_mask, n, d_dist_out, st);
+        case 2: return launch_bfs_rw<2>(env, d_env_ids, d_mask, n, d_dist_out, st);
+        case 3: return launch_bfs_rw<3>(env, d_env_ids, d_mask, n, d_dist_out, st);
+        case 4: return launch_bfs_rw<4>(env, d_env_ids, d_mask, n, d_dist_out, st);
     }
     mapf_set_error("unsupported map size");
     return MAPF_EINVAL;
+}
+
+int mapf_launch_bfs(mapf_env *env, const int32_t *d_env_ids, int n, int32_t *d_dist_out, cudaStream_t st)
+{
+    return launch_bfs(env, d_env_ids, nullptr, n, d_dist_out, st);
+}
+
+// all B slots, skipping those whose mask byte is zero (NULL mask = all)
+int mapf_launch_bfs_masked(mapf_env *env, const uint8_t *d_mask, cudaStream_t st)
+{
+    return launch_bfs(env, nullptr, d_mask, env->d.B, nullptr, st);
 }
 
 int mapf_launch_unpack(mapf_env *env, uint8_t *d_map, uint8_t *d_navi, cudaStream_t st)

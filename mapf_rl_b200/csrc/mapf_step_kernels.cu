@@ -43,6 +43,9 @@ struct StepParams {
 enum : int {
     MAPF_STEPF_NAVI_KEEP = 1,    // heuristic-map loads carry an L2 evict_last policy
     MAPF_STEPF_OBS_POLICY = 2,   // observation stores carry an L2 evict_first policy (else st.global.cs)
+    // diagnosis only (results are WRONG with these set; profiles/step_variants.py uses them to bound the kernel)
+    MAPF_STEPF_DIAG_NO_NAVI = 4,   // skip the heuristic-map loads
+    MAPF_STEPF_DIAG_NO_STORE = 8,  // skip the observation stores
 };
 
 // 4 bits -> 4 bool bytes: bit b lands at bit 8b.  The four shifted copies of x (shifts 0,7,14,21)
@@ -67,10 +70,10 @@ __device__ __forceinline__ uint64_t l2_policy_evict_first()
     asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
     return pol;
 }
-__device__ __forceinline__ uint32_t ldg_policy(const uint32_t *ptr, uint64_t pol)
+__device__ __forceinline__ uint2 ldg_policy(const uint2 *ptr, uint64_t pol)
 {
-    uint32_t v;
-    asm("ld.global.nc.L2::cache_hint.b32 %0, [%1], %2;" : "=r"(v) : "l"(ptr), "l"(pol));
+    uint2 v;
+    asm("ld.global.nc.L2::cache_hint.v2.b32 {%0, %1}, [%2], %3;" : "=r"(v.x), "=r"(v.y) : "l"(ptr), "l"(pol));
     return v;
 }
 __device__ __forceinline__ void stg_policy(uint4 *ptr, const uint4 &v, uint64_t pol)
@@ -325,21 +328,20 @@ step_observe_kernel(const StepParams p)
             uint32_t x0 = 0;
             if (valid[k]) {
                 const int x = px[k], y = py[k];
-                // window rows x-4..x+4 are padded rows x..x+8; columns y-4..y+4 are padded bits y..y+8
-                const uint32_t *nb = p.navi + ((size_t)e * N + a) * d.navi_agent_stride + (size_t)(y >> 3) * d.R + x;
-                uint32_t wa[9], wb[9];
-                if (navi_keep) {
+                // window rows x-4..x+4 are padded rows x..x+8; columns y-4..y+4 are padded bits y..y+8: all inside
+                // navi tile (x >> 3, y >> 3), rows (x & 7) .. (x & 7) + 8 of one 128-byte line
+                const uint2 *nb = reinterpret_cast<const uint2 *>(p.navi + ((size_t)e * N + a) * d.navi_agent_stride) +
+                                  ((size_t)((x >> 3) * d.NB + (y >> 3)) << 4) + (x & 7);
+                uint2 wr[9];
+                if (p.flags & MAPF_STEPF_DIAG_NO_NAVI) {
 #pragma unroll
-                    for (int u = 0; u < 9; ++u) {
-                        wa[u] = ldg_policy(nb + u, pol_keep);
-                        wb[u] = ldg_policy(nb + d.R + u, pol_keep);
-                    }
+                    for (int u = 0; u < 9; ++u) wr[u] = make_uint2(x + u, y);
+                } else if (navi_keep) {
+#pragma unroll
+                    for (int u = 0; u < 9; ++u) wr[u] = ldg_policy(nb + u, pol_keep);
                 } else {
 #pragma unroll
-                    for (int u = 0; u < 9; ++u) {
-                        wa[u] = __ldg(nb + u);
-                        wb[u] = __ldg(nb + d.R + u);
-                    }
+                    for (int u = 0; u < 9; ++u) wr[u] = __ldg(nb + u);
                 }
                 const int sh = y & 7;
                 const uint32_t *ag_row = s_agent + x * RWS, *ob_row = s_obst + x * RWS;
@@ -353,9 +355,10 @@ step_observe_kernel(const StepParams p)
                     } else if constexpr (c == 1) {
                         return window9(ob_row + u * RWS, y);
                     } else {
-                        // byte c-2 of wa / wb = direction c-2 bits of columns 8cb.. / 8cb+8..
-                        constexpr uint32_t sel = 0x0040u + 0x11u * (c - 2);
-                        return (__byte_perm(wa[u], wb[u], sel) >> sh) & 0x1ffu;
+                        // direction dd = c - 2: 16 column bits at bit 16 dd of the tile row
+                        constexpr int dd = c - 2;
+                        const uint32_t half = dd < 2 ? wr[u].x : wr[u].y;
+                        return (half >> (sh + 16 * (dd & 1))) & 0x1ffu;
                     }
                 };
                 auto emit = [&](auto mc, uint32_t w) {
@@ -391,7 +394,9 @@ step_observe_kernel(const StepParams p)
                 v.z = expand4((s >> 8) & 0xfu);
                 v.w = expand4(s >> 12);
                 uint4 *dst = reinterpret_cast<uint4 *>(obase + (c << 4));
-                if (obs_policy) stg_policy(dst, v, pol_stream);
+                if (p.flags & MAPF_STEPF_DIAG_NO_STORE) {
+                    if (v.x == 0xdeadbeefu) __stcs(dst, v);  // never true: keeps the expansion alive
+                } else if (obs_policy) stg_policy(dst, v, pol_stream);
                 else __stcs(dst, v);
             }
             // ragged first / last chunk of an unaligned observation block

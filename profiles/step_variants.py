@@ -94,7 +94,8 @@ def main():
         child(args)
         return
     for spec in args.variants.split(","):
-        v, f = spec.split(":")
+        parts = spec.split(":")
+        v, f = parts[0], parts[1]
         env = dict(os.environ, MAPF_STEP_VARIANT=v, MAPF_STEP_FLAGS=f)
         cmd = [sys.executable, os.path.abspath(__file__), "--child", "--envs", str(args.envs), "--agents", str(args.agents),
                "--side", str(args.side), "--steps", str(args.steps)]
