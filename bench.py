@@ -186,11 +186,9 @@ def workload_name(args):
 def run_ours(args):
     import torch
     import torch.distributed as dist
-    from mapf_rl_b200 import BatchedEnvironment
+    from mapf_rl_b200 import BatchedEnvironment, sharding
 
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
+    rank, world, local = sharding.rank_world()
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
     torch.cuda.set_device(local)
@@ -200,9 +198,11 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
 
     B, N, L = args.num_envs, args.num_agents, args.map_length
-    maps, agents, goals = make_instances(B, L, N, args.density, args.seed, rank * B)
     env = BatchedEnvironment(B, N, L, device=dev)
-    env.load(maps, agents, goals)
+    # synthetic instances drawn on the device by the reference's procedure (environment.py:100-138) at fixed
+    # density; slot e of rank r is global environment r*B + e whatever the number of GPUs (weak scaling)
+    env.reset(seed=args.seed, env_offset=sharding.weak_offset(B, rank), density=args.density)
+    env.check()
 
     R = args.obs_ring  # observation ring (device replay slots): R x B*N*486 bytes > L2
     replay = torch.empty((R, B, N, 6, 9, 9), dtype=torch.uint8, device=dev)
@@ -229,7 +229,7 @@ def run_ours(args):
         torch.cuda.synchronize(dev)
     env.check()
 
-    # ---- timed region: exactly K steps, device-resident inputs --------------------------------
+    # ---- timed region: exactly K steps, device-resident inputs, one kernel launch per step ------
     sampler = ClockSampler(local)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
@@ -240,11 +240,7 @@ def run_ours(args):
     ev1.record()
     barrier()
     clocks = sampler.stop()
-    ms = ev0.elapsed_time(ev1)
-    t = torch.tensor([ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms = float(t.item())
+    ms = sharding.max_over_ranks(ev0.elapsed_time(ev1), dev)
     value = world * B * N * args.steps / (ms * 1e-3)
 
     # ---- e2e: through the host-buffer C-ABI entry point (mapf_env_step_host) ---------------------
@@ -254,11 +250,8 @@ def run_ours(args):
         for s in range(steps):
             env.step_host(actions_host[s % A], want_obs=want_obs, device_obs=replay[s % R])
         torch.cuda.synchronize(dev)
-        el = time.perf_counter() - t0
-        tt = torch.tensor([el], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        return world * B * N * steps / float(tt.item())
+        el = sharding.max_over_ranks(time.perf_counter() - t0, dev)
+        return world * B * N * steps / el
 
     e2e_steps = max(10, min(args.steps, 400))
     e2e_run(3, False)
@@ -266,7 +259,22 @@ def run_ours(args):
     e2e_run(1, True)
     e2e_obs_value = e2e_run(max(3, min(args.steps, 20)), True)
 
+    # context for the roofline: what a write-only stream of the same size reaches on this GPU
+    def write_probe():
+        buf = replay.view(-1)
+        for _ in range(3):
+            buf.zero_()
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(10):
+            buf.zero_()
+        e1.record()
+        torch.cuda.synchronize(dev)
+        return buf.numel() * 10 / (e0.elapsed_time(e1) * 1e-3) / 1e9
+
     line = None
+    probe = write_probe()
     if rank == 0:
         peak, peak_src = measured_hbm_peak()
         per_launch_s = ms * 1e-3 / args.steps
@@ -283,6 +291,7 @@ def run_ours(args):
             "dtype": "u8", "data": "synthetic",
             "config": {"workload": workload_name(args), "num_envs_per_gpu": B, "num_agents": N, "map_length": L,
                        "obstacle_density": args.density, "actions": "uniform iid {0..4}, 16 pre-generated device tensors",
+                       "instances": "device-side generator (mapf_env_reset), global env index = rank*B + slot",
                        "l2": f"no flush: per-step output {B * N * 486 / 1e6:.0f} MB rotates over a {R}-slot device ring "
                              f"({R * B * N * 486 / 1e6:.0f} MB) + {env.arena_bytes / 1e6:.0f} MB state arena, both > 126 MB L2",
                        "extra_warmup": "0.3 s of untimed steps after W so SM clocks are under load"},
@@ -295,10 +304,17 @@ def run_ours(args):
                              "d2h_bytes_per_step": B * N * 4 + B * 5 + B * N * 486,
                              "api": "same call with the full observation tensor also copied to host (drop-in Environment.step)"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "kernel": "step_observe_kernel<2,1,true>",
-                         "algorithmic_bytes_per_agent_step": algo_bytes(N, L), "peak_source": peak_src},
+                         "traffic": traffic, "kernel": "step_observe_kernel<RW=2,K=1,DO_STEP,4 warps,12 CTAs/SM>",
+                         "algorithmic_bytes_per_agent_step": algo_bytes(N, L), "peak_source": peak_src,
+                         "write_only_probe_GBs": probe,
+                         "note": "peak = measured copy (read+write) bandwidth; write_only_probe_GBs = torch zero_() over the "
+                                 "observation ring on this GPU, the ceiling of a write-dominated kernel"},
         }
         if not args.no_cpu_baseline and world == 1:
+            S = min(2048, B)
+            maps = env.map[:S].cpu().numpy()
+            agents = env.agents_pos[:S].cpu().numpy()
+            goals = env.goals_pos[:S].cpu().numpy()
             line["cpu_baseline"] = cpu_baseline(maps, agents, goals, N, L, seconds=args.cpu_seconds)
         print(json.dumps(line), flush=True)
     if world > 1:

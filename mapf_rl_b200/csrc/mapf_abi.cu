@@ -118,6 +118,8 @@ int mapf_env_create(const mapf_env_config *cfg, mapf_env **out)
     d.obst_stride = (d.R * d.RWS + 3) & ~3;
     d.navi_agent_stride = d.NB * d.NB * 32;
     env->device = cfg->device;
+    env->num_sms = 148;
+    cudaDeviceGetAttribute(&env->num_sms, cudaDevAttrMultiProcessorCount, cfg->device);
     for (int i = 0; i < 5; ++i) env->reward[i] = cfg->reward_fn[i];
 
     int rc = MAPF_OK;

@@ -42,6 +42,7 @@ struct EnvDims {
 struct mapf_env {
     EnvDims d;
     int device;
+    int num_sms;
     float reward[5];
     uint32_t *obst;
     uint8_t *pos;

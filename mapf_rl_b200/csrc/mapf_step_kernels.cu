@@ -420,16 +420,18 @@ step_observe_kernel(const StepParams p)
 
 // ---- launch plumbing ---------------------------------------------------------------------------
 struct StepTuning {
-    int variant;  // CTA shape / register cap of the (RW = 2, K = 1) instantiation, see launch_step_rwk
+    int variant;       // CTA shape / register cap of the (RW = 2, K = 1) instantiation, see launch_step_rwk
     int flags;
+    int ctas_per_sm;   // > 0: persistent grid of that many CTAs per SM, each warp strides over environments
 };
 
 const StepTuning &tuning()
 {
     static const StepTuning t = [] {
-        StepTuning r{1, MAPF_STEPF_NAVI_KEEP};
+        StepTuning r{1, MAPF_STEPF_NAVI_KEEP, 0};
         if (const char *s = std::getenv("MAPF_STEP_VARIANT")) r.variant = std::atoi(s);
         if (const char *s = std::getenv("MAPF_STEP_FLAGS")) r.flags = std::atoi(s);
+        if (const char *s = std::getenv("MAPF_STEP_CTAS_PER_SM")) r.ctas_per_sm = std::atoi(s);
         return r;
     }();
     return t;
@@ -446,7 +448,11 @@ int launch_step_cfg(const mapf_env *env, StepParams &p, cudaStream_t st)
     }
     if (smem > 48 * 1024)  // per-device attribute; cheap enough to set on every large-smem launch
         MAPF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const int grid = (env->d.B + WARPS - 1) / WARPS;
+    int grid = (env->d.B + WARPS - 1) / WARPS;
+    if (tuning().ctas_per_sm > 0) {
+        const int cap = env->num_sms * tuning().ctas_per_sm;
+        if (grid > cap) grid = cap;
+    }
     kern<<<grid, WARPS * 32, smem, st>>>(p);
     MAPF_CUDA(cudaGetLastError());
     return MAPF_OK;

@@ -76,7 +76,7 @@ def child(args):
         us = ev0.elapsed_time(ev1) * 1e3 / args.steps
         best = us if best is None else min(best, us)
     env.check()
-    print(json.dumps({"variant": os.environ.get("MAPF_STEP_VARIANT"), "flags": os.environ.get("MAPF_STEP_FLAGS"),
+    print(json.dumps({"variant": os.environ.get("MAPF_STEP_VARIANT"), "flags": os.environ.get("MAPF_STEP_FLAGS"), "ctas_per_sm": os.environ.get("MAPF_STEP_CTAS_PER_SM"),
                       "us_per_step": round(best, 2), "G_agent_steps_s": round(B * N / best / 1e3, 3),
                       "parity16": ok, "B": B, "N": N, "L": L}), flush=True)
 
@@ -97,6 +97,8 @@ def main():
         parts = spec.split(":")
         v, f = parts[0], parts[1]
         env = dict(os.environ, MAPF_STEP_VARIANT=v, MAPF_STEP_FLAGS=f)
+        if len(parts) > 2:
+            env["MAPF_STEP_CTAS_PER_SM"] = parts[2]
         cmd = [sys.executable, os.path.abspath(__file__), "--child", "--envs", str(args.envs), "--agents", str(args.agents),
                "--side", str(args.side), "--steps", str(args.steps)]
         r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=600)
