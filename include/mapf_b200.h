@@ -105,8 +105,10 @@ int mapf_env_observe(mapf_env *env, uint8_t *d_obs, uint8_t *d_pos, void *stream
 
 /* Host-buffer variant of step (what a per-process actor calls): copies actions H2D, runs the fused
  * kernel, copies rewards / done / steps (and obs if h_obs != NULL) D2H, then synchronises.
- * All h_* buffers are ordinary or pinned host memory.  d_obs_opt: if non-NULL the observation is
- * written there (device replay tensor) instead of an internal buffer. */
+ * All h_* buffers are ordinary or page-locked host memory; page-locked ones (cudaHostAlloc /
+ * cudaHostRegister / torch pin_memory) are used as DMA endpoints directly, pageable ones are staged through
+ * the handle's own pinned area.  d_obs_opt: if non-NULL the observation is written there (device replay
+ * tensor) instead of an internal buffer. */
 int mapf_env_step_host(mapf_env *env, const uint8_t *h_actions, uint8_t *h_obs, float *h_rewards,
                        uint8_t *h_done, int32_t *h_steps, uint8_t *d_obs_opt, void *stream);
 

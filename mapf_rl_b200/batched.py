@@ -137,20 +137,37 @@ class BatchedEnvironment:
                                                  self._stream()))
         return obs, pos
 
-    def step_host(self, actions: np.ndarray, want_obs: bool = False, device_obs=None):
-        """Host-buffer step through mapf_env_step_host: numpy in, numpy out, synchronous."""
+    def _host_buffers(self, want_obs: bool):
+        """Page-locked host endpoints of step_host, allocated once and reused (DMA straight into them)."""
+        torch = _torch()
         B, N = self.num_envs, self.num_agents
-        a = np.ascontiguousarray(actions, dtype=np.uint8)
+        hb = getattr(self, "_hb", None)
+        if hb is None:
+            hb = dict(actions=torch.empty((B, N), dtype=torch.uint8, pin_memory=True),
+                      rewards=torch.empty((B, N), dtype=torch.float32, pin_memory=True),
+                      done=torch.empty((B,), dtype=torch.uint8, pin_memory=True),
+                      steps=torch.empty((B,), dtype=torch.int32, pin_memory=True))
+            hb.update({k + "_np": v.numpy() for k, v in list(hb.items())})
+            self._hb = hb
+        if want_obs and "obs" not in hb:
+            hb["obs"] = torch.empty((B, N, *self.OBS_SHAPE), dtype=torch.uint8, pin_memory=True)
+            hb["obs_np"] = hb["obs"].numpy()
+        return hb
+
+    def step_host(self, actions: np.ndarray, want_obs: bool = False, device_obs=None):
+        """Host-buffer step through mapf_env_step_host: numpy in, numpy out, synchronous.
+        Returns (obs | None, rewards, done, steps) as numpy VIEWS of page-locked buffers owned by this object:
+        they are overwritten by the next step_host call (copy them to keep them)."""
+        B, N = self.num_envs, self.num_agents
+        hb = self._host_buffers(want_obs)
+        a = np.asarray(actions)
         assert a.shape == (B, N), "actions number"
-        rewards = np.empty((B, N), dtype=np.float32)
-        done = np.empty((B,), dtype=np.uint8)
-        steps = np.empty((B,), dtype=np.int32)
-        obs = np.empty((B, N, *self.OBS_SHAPE), dtype=np.uint8) if want_obs else None
+        np.copyto(hb["actions_np"], a, casting="unsafe")
         _native.check(self._lib.mapf_env_step_host(
-            self._h, a.ctypes.data_as(C.c_void_p), obs.ctypes.data_as(C.c_void_p) if want_obs else None,
-            rewards.ctypes.data_as(C.c_void_p), done.ctypes.data_as(C.c_void_p), steps.ctypes.data_as(C.c_void_p),
+            self._h, hb["actions"].data_ptr(), hb["obs"].data_ptr() if want_obs else None,
+            hb["rewards"].data_ptr(), hb["done"].data_ptr(), hb["steps"].data_ptr(),
             C.c_void_p(device_obs.data_ptr()) if device_obs is not None else None, self._stream()))
-        return obs, rewards, done, steps
+        return (hb["obs_np"] if want_obs else None), hb["rewards_np"], hb["done_np"], hb["steps_np"]
 
     def check(self):
         """Synchronous: raise if a kernel latched an error (bad action -> AssertionError like the reference)."""

@@ -47,6 +47,16 @@ struct DeviceGuard {
     }
 };
 
+bool host_is_pinned(const void *p)
+{
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();  // clear: an unregistered pointer is not an error for us
+        return false;
+    }
+    return a.type == cudaMemoryTypeHost;
+}
+
 template <typename T>
 int dev_alloc(T **p, size_t count, int64_t *total)
 {
@@ -259,23 +269,36 @@ int mapf_env_step_host(mapf_env *env, const uint8_t *h_actions, uint8_t *h_obs, 
 
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     uint8_t *obs_dev = d_obs_opt ? d_obs_opt : env->d_obs;
-    // pinned layout: actions u8[BN] | pad to 4 | rewards f32[BN] | steps i32[B] | done u8[B]
+    // pinned layout: actions u8[BN] | pad to 16 | rewards f32[BN] | steps i32[B] | done u8[B]
     uint8_t *pin_act = env->h_pinned;
     float *pin_rew = reinterpret_cast<float *>(env->h_pinned + ((BN + 15) & ~(size_t)15));
     int32_t *pin_steps = reinterpret_cast<int32_t *>(pin_rew + BN);
     uint8_t *pin_done = reinterpret_cast<uint8_t *>(pin_steps + d.B);
-    std::memcpy(pin_act, h_actions, BN);
-    MAPF_CUDA(cudaMemcpyAsync(env->d_actions, pin_act, BN, cudaMemcpyHostToDevice, st));
+    // page-locked caller buffers are used as DMA endpoints directly; pageable ones go through the handle's
+    // pinned staging area (one extra host memcpy each way)
+    const bool act_direct = host_is_pinned(h_actions);
+    const bool out_direct = host_is_pinned(h_rewards) && host_is_pinned(h_done) && (!h_steps || host_is_pinned(h_steps));
+    const uint8_t *src_act = h_actions;
+    if (!act_direct) {
+        std::memcpy(pin_act, h_actions, BN);
+        src_act = pin_act;
+    }
+    float *dst_rew = out_direct ? h_rewards : pin_rew;
+    uint8_t *dst_done = out_direct ? h_done : pin_done;
+    int32_t *dst_steps = out_direct ? h_steps : pin_steps;
+    MAPF_CUDA(cudaMemcpyAsync(env->d_actions, src_act, BN, cudaMemcpyHostToDevice, st));
     rc = mapf_launch_step(env, env->d_actions, obs_dev, env->d_rewards, env->d_done, env->d_steps_out, st);
     if (rc != MAPF_OK) return rc;
-    MAPF_CUDA(cudaMemcpyAsync(pin_rew, env->d_rewards, BN * 4, cudaMemcpyDeviceToHost, st));
-    MAPF_CUDA(cudaMemcpyAsync(pin_steps, env->d_steps_out, (size_t)d.B * 4, cudaMemcpyDeviceToHost, st));
-    MAPF_CUDA(cudaMemcpyAsync(pin_done, env->d_done, (size_t)d.B, cudaMemcpyDeviceToHost, st));
+    MAPF_CUDA(cudaMemcpyAsync(dst_rew, env->d_rewards, BN * 4, cudaMemcpyDeviceToHost, st));
+    if (dst_steps) MAPF_CUDA(cudaMemcpyAsync(dst_steps, env->d_steps_out, (size_t)d.B * 4, cudaMemcpyDeviceToHost, st));
+    MAPF_CUDA(cudaMemcpyAsync(dst_done, env->d_done, (size_t)d.B, cudaMemcpyDeviceToHost, st));
     if (h_obs) MAPF_CUDA(cudaMemcpyAsync(h_obs, obs_dev, BN * MAPF_OBS_BYTES_PER_AGENT, cudaMemcpyDeviceToHost, st));
     MAPF_CUDA(cudaStreamSynchronize(st));
-    std::memcpy(h_rewards, pin_rew, BN * 4);
-    std::memcpy(h_done, pin_done, (size_t)d.B);
-    if (h_steps) std::memcpy(h_steps, pin_steps, (size_t)d.B * 4);
+    if (!out_direct) {
+        std::memcpy(h_rewards, pin_rew, BN * 4);
+        std::memcpy(h_done, pin_done, (size_t)d.B);
+        if (h_steps) std::memcpy(h_steps, pin_steps, (size_t)d.B * 4);
+    }
     return MAPF_OK;
 }
 

@@ -262,3 +262,75 @@ def test_step_host_entry_point():
         assert np.array_equal(oo.astype(np.uint8), obs[k])
         assert np.array_equal(np.asarray(orw, dtype=np.float32), rew[k])
         assert int(od) == done[k] and steps[k] == 1
+
+
+def test_step_host_pageable_caller_buffers():
+    """mapf_env_step_host with ordinary (pageable) numpy buffers goes through the handle's pinned staging area."""
+    import ctypes as C
+    from mapf_rl_b200 import _native
+    maps, agents, goals = instances(32)
+    env = make_env(3, 32, 40)
+    env.load(maps[:3], agents[:3], goals[:3])
+    acts = np.random.default_rng(5).integers(0, 5, size=(3, 32)).astype(np.uint8)
+    rew = np.zeros((3, 32), dtype=np.float32)
+    done = np.zeros(3, dtype=np.uint8)
+    steps = np.zeros(3, dtype=np.int32)
+    obs = np.zeros((3, 32, 6, 9, 9), dtype=np.uint8)
+    vp = lambda a: a.ctypes.data_as(C.c_void_p)
+    _native.check(env._lib.mapf_env_step_host(env._h, vp(acts), vp(obs), vp(rew), vp(done), vp(steps), None, env._stream()))
+    for k in range(3):
+        o = oracle.OracleEnv()
+        o.load(maps[k], agents[k], goals[k])
+        (oo, op), orw, od, _ = o.step(acts[k])
+        assert np.array_equal(oo.astype(np.uint8), obs[k])
+        assert np.array_equal(np.asarray(orw, dtype=np.float32), rew[k])
+        assert int(od) == done[k] and steps[k] == 1
+
+
+def test_full_size_batch_properties():
+    """BASELINE configs[1] size (8192 envs x 32 agents): size-independent properties + sampled oracle parity.
+    The batch tiles the 200 pkl instances, so replicas of an instance driven by the same actions must agree
+    bit for bit wherever they sit in the batch."""
+    import torch
+    maps, agents, goals = instances(32)
+    B, N, T = 8192, 32, 24
+    rep = np.arange(B) % 200
+    env = make_env(B, N, 40)
+    env.load(maps[rep], agents[rep], goals[rep])
+    rng = np.random.default_rng(99)
+    sample = rng.choice(B, size=48, replace=False)
+    sidx = torch.as_tensor(sample, device="cuda:0")
+    ora = {}
+    for k in sample:
+        o = oracle.OracleEnv()
+        o.load(maps[rep[k]], agents[rep[k]], goals[rep[k]])
+        ora[k] = o
+    base_acts = rng.integers(0, 5, size=(T, 200, N)).astype(np.uint8)
+    for s in range(T):
+        acts = base_acts[s][rep]
+        obs, rew, done = env.step(acts)
+        pos = env.agents_pos
+        # replicas agree (no cross-env interference, no dependence on the slot / CTA / warp an env lands in)
+        o4 = obs.view(B, -1)
+        assert torch.equal(o4[200:400], o4[:200]) and torch.equal(o4[8000:8192], o4[:192])
+        assert torch.equal(rew[4000:4200], rew[:200]) and torch.equal(pos[8000:8192], pos[:192])
+        # bool bytes only; the centre of channel 0 is cleared; agent cells unique (environment.py:424-428)
+        assert int(obs.max().item()) <= 1
+        assert int(obs[:, :, 0, 4, 4].sum().item()) == 0
+        cells = pos[..., 0].to(torch.int64) * 40 + pos[..., 1].to(torch.int64)
+        assert int((torch.sort(cells, dim=1).values.diff(dim=1) == 0).sum().item()) == 0
+        # channel 0 counts ordered pairs of agents within each other's 9x9 window
+        dx = (pos[:, :, None, 0].to(torch.int32) - pos[:, None, :, 0].to(torch.int32)).abs()
+        dy = (pos[:, :, None, 1].to(torch.int32) - pos[:, None, :, 1].to(torch.int32)).abs()
+        near = ((dx <= 4) & (dy <= 4)).sum((1, 2)) - N
+        assert torch.equal(obs[:, :, 0].to(torch.int64).sum((1, 2, 3)), near)
+        # observe() is idempotent and equals what step() returned
+        if s % 8 == 0:
+            again, p2 = env.observe()
+            assert torch.equal(again, obs) and torch.equal(p2, pos)
+        obs_h, rew_h, pos_h, done_h = (t[sidx].cpu().numpy() for t in (obs, rew, pos, done))
+        for q, k in enumerate(sample):
+            (oo, op), orw, od, _ = ora[k].step(acts[k])
+            assert np.array_equal(oo.astype(np.uint8), obs_h[q]) and np.array_equal(op, pos_h[q])
+            assert np.array_equal(np.asarray(orw, dtype=np.float32), rew_h[q]) and int(od) == done_h[q]
+    env.check()
