@@ -335,7 +335,7 @@ def main():
     ap.add_argument("--density", type=float, default=0.3)
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--obs-ring", type=int, default=4)
-    ap.add_argument("--ref-envs", type=int, default=1024)
+    ap.add_argument("--ref-envs", type=int, default=4096)
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

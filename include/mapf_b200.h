@@ -112,6 +112,13 @@ int mapf_env_observe(mapf_env *env, uint8_t *d_obs, uint8_t *d_pos, void *stream
 int mapf_env_step_host(mapf_env *env, const uint8_t *h_actions, uint8_t *h_obs, float *h_rewards,
                        uint8_t *h_done, int32_t *h_steps, uint8_t *d_obs_opt, void *stream);
 
+/* ---- communication mask of Network.step (model.py:196-208), the actor-side glue next to observe() ------
+ *   d_mask_out u8[B, N, N]: mask[i][j] = 1 iff agent j is inside agent i's 9x9 field of view (|dx| <= 4 and
+ *   |dy| <= 4) AND j is one of the `max_comm_agents` (config.py:58, 1..3) nearest agents of i by Euclidean
+ *   distance, i itself included.  torch.topk's order among equal distances is unspecified; ties go to
+ *   the lower agent id here. */
+int mapf_env_comm_mask(mapf_env *env, int32_t max_comm_agents, uint8_t *d_mask_out, void *stream);
+
 /* ---- state access (attributes read by worker.py:390,426 / test.py:46-48,130) --------------- */
 /* Any output pointer may be NULL.  d_map u8[B,L,L]; d_pos/d_goals u8[B,N,2]; d_steps i32[B];
  * d_navi u8[B,N,4,L,L] = navi_map without the obs_radius padding (environment.py:253-276). */

@@ -137,6 +137,16 @@ class BatchedEnvironment:
                                                  self._stream()))
         return obs, pos
 
+    def comm_mask(self, max_comm_agents: int = config.max_comm_agents, out=None):
+        """-> uint8[B,N,N] communication mask of Network.step (model.py:196-208) for the current positions:
+        in each other's field of view AND among the `max_comm_agents` nearest (self included; ties -> lower id)."""
+        torch = _torch()
+        B, N = self.num_envs, self.num_agents
+        m = out if out is not None else torch.empty((B, N, N), dtype=torch.uint8, device=self.device)
+        assert m.is_contiguous() and m.dtype == torch.uint8 and m.numel() == B * N * N
+        _native.check(self._lib.mapf_env_comm_mask(self._h, int(max_comm_agents), C.c_void_p(m.data_ptr()), self._stream()))
+        return m
+
     def _host_buffers(self, want_obs: bool):
         """Page-locked host endpoints of step_host, allocated once and reused (DMA straight into them)."""
         torch = _torch()

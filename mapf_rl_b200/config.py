@@ -24,6 +24,10 @@ prioritized_replay_alpha = 0.6
 prioritized_replay_beta = 0.4
 forward_steps = 2
 latent_dim = 256
+max_comm_agents = 3      # config.py:58, including the agent itself
+max_num_agents = 6       # config.py:51 (spelled max_num_agetns there)
+max_map_length = 40      # config.py:52
+learning_starts = 50000  # config.py:26
 
 # adaptive curriculum start (config.py:49)
 init_set = (1, 10)

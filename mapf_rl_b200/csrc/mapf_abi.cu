@@ -14,6 +14,7 @@ int mapf_launch_bfs(mapf_env *, const int32_t *, int, int32_t *, cudaStream_t);
 int mapf_launch_step(mapf_env *, const uint8_t *, uint8_t *, float *, uint8_t *, int32_t *, cudaStream_t);
 int mapf_launch_observe(mapf_env *, uint8_t *, uint8_t *, cudaStream_t);
 int mapf_launch_unpack(mapf_env *, uint8_t *, uint8_t *, cudaStream_t);
+int mapf_launch_comm_mask(mapf_env *, int, uint8_t *, cudaStream_t);
 int mapf_launch_reset(mapf_env *, const uint8_t *, uint64_t, uint64_t, float, cudaStream_t);
 int mapf_launch_per_update(mapf_per *, PerScratch *, const int64_t *, const double *, int64_t, cudaStream_t);
 int mapf_launch_per_sample(mapf_per *, const double *, int64_t, int64_t *, double *, float *, double, cudaStream_t);
@@ -300,6 +301,16 @@ int mapf_env_step_host(mapf_env *env, const uint8_t *h_actions, uint8_t *h_obs, 
         if (h_steps) std::memcpy(h_steps, pin_steps, (size_t)d.B * 4);
     }
     return MAPF_OK;
+}
+
+int mapf_env_comm_mask(mapf_env *env, int32_t max_comm_agents, uint8_t *d_mask_out, void *stream)
+{
+    REQUIRE_ENV(env);
+    if (!d_mask_out || max_comm_agents < 1 || max_comm_agents > 3) {
+        mapf_set_error("mapf_env_comm_mask: NULL buffer or max_comm_agents outside 1..3 (config.py:58)");
+        return MAPF_EINVAL;
+    }
+    return mapf_launch_comm_mask(env, max_comm_agents, d_mask_out, static_cast<cudaStream_t>(stream));
 }
 
 int mapf_env_get_state(mapf_env *env, uint8_t *d_map, uint8_t *d_pos, uint8_t *d_goals, int32_t *d_steps, uint8_t *d_navi,

@@ -183,6 +183,64 @@ bfs_navi_kernel(EnvDims d, const int32_t *__restrict__ env_ids, const uint8_t *_
 }
 
 // ---------------------------------------------------------------------------------------------
+// communication mask of the actor-side inference glue                    (model.py:196-208)
+//
+// comm_mask[i][j] = (|dx| <= obs_radius and |dy| <= obs_radius) and j is among the k nearest agents of i
+// (Euclidean, i itself included at distance 0).  torch.topk leaves the order of equal distances
+// unspecified; here ties go to the lower agent id (key = d^2 << 8 | j).  One warp per environment,
+// lane = agent; positions of the env sit in shared memory.
+// ---------------------------------------------------------------------------------------------
+constexpr int kCommWarps = 4;
+
+__global__ void __launch_bounds__(kCommWarps * 32)
+comm_mask_kernel(EnvDims d, const uint8_t *__restrict__ pos, int k_nearest, uint8_t *__restrict__ out)
+{
+    __shared__ uint16_t s_pos[kCommWarps][MAPF_MAX_AGENTS];
+    __shared__ uint32_t s_bits[kCommWarps][MAPF_MAX_AGENTS][MAPF_MAX_AGENTS / 32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int e = blockIdx.x * kCommWarps + warp;
+    if (e >= d.B) return;
+    const int N = d.N;
+    for (int a = lane; a < N; a += 32) s_pos[warp][a] = reinterpret_cast<const uint16_t *>(pos)[(size_t)e * N + a];
+    __syncwarp();
+    for (int i = lane; i < N; i += 32) {
+        const int xi = s_pos[warp][i] & 0xff, yi = s_pos[warp][i] >> 8;
+        uint32_t b0 = 0xffffffffu, b1 = 0xffffffffu, b2 = 0xffffffffu;  // three smallest keys, ascending
+        for (int j = 0; j < N; ++j) {
+            const int dx = xi - (s_pos[warp][j] & 0xff), dy = yi - (s_pos[warp][j] >> 8);
+            uint32_t key = ((uint32_t)(dx * dx + dy * dy) << 8) | (uint32_t)j;
+            if (key < b2) {
+                b2 = key;
+                if (b2 < b1) { const uint32_t t = b1; b1 = b2; b2 = t; }
+                if (b1 < b0) { const uint32_t t = b0; b0 = b1; b1 = t; }
+            }
+        }
+        uint32_t row[MAPF_MAX_AGENTS / 32] = {0, 0, 0, 0};
+        const uint32_t best[3] = {b0, b1, b2};
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+            if (q < k_nearest && best[q] != 0xffffffffu) {
+                const int j = best[q] & 0xff;
+                const int dx = abs(xi - (s_pos[warp][j] & 0xff)), dy = abs(yi - (s_pos[warp][j] >> 8));
+                if (dx <= MAPF_OBS_RADIUS && dy <= MAPF_OBS_RADIUS) {
+#pragma unroll
+                    for (int w = 0; w < MAPF_MAX_AGENTS / 32; ++w)
+                        if ((j >> 5) == w) row[w] |= 1u << (j & 31);
+                }
+            }
+        }
+#pragma unroll
+        for (int w = 0; w < MAPF_MAX_AGENTS / 32; ++w) s_bits[warp][i][w] = row[w];
+    }
+    __syncwarp();
+    uint8_t *o = out + (size_t)e * N * N;
+    for (int idx = lane; idx < N * N; idx += 32) {
+        const int i = idx / N, j = idx - i * N;
+        o[idx] = (s_bits[warp][i][j >> 5] >> (j & 31)) & 1u;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // attribute reads: unpack state for parity dumps / drop-in attributes
 // ---------------------------------------------------------------------------------------------
 __global__ void unpack_map_kernel(EnvDims d, const uint32_t *__restrict__ obst, uint8_t *__restrict__ map_out)
@@ -265,6 +323,14 @@ int mapf_launch_bfs(mapf_env *env, const int32_t *d_env_ids, int n, int32_t *d_d
 int mapf_launch_bfs_masked(mapf_env *env, const uint8_t *d_mask, cudaStream_t st)
 {
     return launch_bfs(env, nullptr, d_mask, env->d.B, nullptr, st);
+}
+
+int mapf_launch_comm_mask(mapf_env *env, int k_nearest, uint8_t *d_out, cudaStream_t st)
+{
+    const int grid = (env->d.B + kCommWarps - 1) / kCommWarps;
+    comm_mask_kernel<<<grid, kCommWarps * 32, 0, st>>>(env->d, env->pos, k_nearest, d_out);
+    MAPF_CUDA(cudaGetLastError());
+    return MAPF_OK;
 }
 
 int mapf_launch_unpack(mapf_env *env, uint8_t *d_map, uint8_t *d_navi, cudaStream_t st)

@@ -256,6 +256,21 @@ void mo_observe(int L, int N, int r, const uint8_t *map, const int32_t *pos, con
 /* B independent envs (same L, N), T steps, actions u8[T*B*N]; obs of the last step kept.  */
 /* Returns the number of agent-steps executed.  Parallel over envs when built with OpenMP  */
 /* (each env is independent, exactly like one reference Environment per actor process).    */
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+/* host threads used by mo_rollout (the batched CPU baseline); returns the count in effect */
+int mo_set_threads(int n)
+{
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+    return omp_get_max_threads();
+#else
+    (void)n;
+    return 1;
+#endif
+}
+
 long mo_rollout(int B, int L, int N, int r, int T, const uint8_t *maps, int32_t *pos, const int32_t *goals,
                 const uint8_t *navi, const uint8_t *actions, const double *reward_fn,
                 float *rewards_out, uint8_t *done_out, uint8_t *obs_out)
@@ -375,3 +390,35 @@ void mo_learner_td(int64_t n, const float *q_online, const float *q_target_next,
 }
 
 int mo_abi_version(void) { return 1; }
+
+/* ------------------------------------------------------------------------------------------ */
+/* Communication mask of Network.step — model.py:196-208                                       */
+/* pos: int32[N*2]; k = min(config.max_comm_agents, N); out: u8[N*N].                           */
+/* Ranking by Euclidean distance (d^2 here: sqrt is monotonic); torch.topk leaves ties          */
+/* unspecified — this restatement (like the CUDA kernel) gives them to the lower agent id.      */
+/* ------------------------------------------------------------------------------------------ */
+void mo_comm_mask(int N, const int32_t *pos, int k, int radius, uint8_t *out)
+{
+    int *used = (int *)malloc(sizeof(int) * (size_t)N);
+    for (int i = 0; i < N; ++i) {
+        memset(used, 0, sizeof(int) * (size_t)N);
+        for (int j = 0; j < N; ++j) out[i * N + j] = 0;
+        for (int q = 0; q < k && q < N; ++q) { /* selection of the q-th nearest, stable in j */
+            int best = -1;
+            long bd = 0;
+            for (int j = 0; j < N; ++j) {
+                if (used[j]) continue;
+                long dx = pos[2 * i] - pos[2 * j], dy = pos[2 * i + 1] - pos[2 * j + 1];
+                long dd = dx * dx + dy * dy;
+                if (best < 0 || dd < bd) {
+                    best = j;
+                    bd = dd;
+                }
+            }
+            used[best] = 1;
+            int adx = abs(pos[2 * i] - pos[2 * best]), ady = abs(pos[2 * i + 1] - pos[2 * best + 1]);
+            if (adx <= radius && ady <= radius) out[i * N + best] = 1; /* :201 in_obs_mask AND :206 */
+        }
+    }
+    free(used);
+}

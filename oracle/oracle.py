@@ -56,6 +56,10 @@ def lib():
         L.mo_actor_td.argtypes = [C.c_int, C.c_int, f64p, f32p, u8p, f64p]
         L.mo_learner_td.restype = None
         L.mo_learner_td.argtypes = [C.c_int64, f32p, f32p, i64p, f32p, f32p, f32p, f32p, f32p]
+        L.mo_set_threads.restype = C.c_int
+        L.mo_set_threads.argtypes = [C.c_int]
+        L.mo_comm_mask.restype = None
+        L.mo_comm_mask.argtypes = [C.c_int, i32p, C.c_int, C.c_int, u8p]
         _lib = L
     return _lib
 
@@ -127,7 +131,7 @@ def rollout(maps, pos, goals, navi_maps, actions, reward_fn=None, obs_radius=4, 
             want_rewards=True):
     """Lockstep batch: maps u8[B,L,L], pos/goals i32[B,N,2] (pos updated in place), navi u8[B,N,4,L,L],
     actions u8[T,B,N].  Returns (rewards f32[T,B,N] | None, done u8[T,B], obs u8[B,N,6,F,F] of last step).
-    `threads` python threads each run a contiguous slice of envs (ctypes releases the GIL)."""
+    `threads` host threads share the environments (OpenMP inside mo_rollout)."""
     B, L = maps.shape[0], maps.shape[1]
     N = pos.shape[1]
     T = actions.shape[0]
@@ -157,10 +161,10 @@ def rollout(maps, pos, goals, navi_maps, actions, reward_fn=None, obs_radius=4, 
             rewards[:, lo:hi] = rw
         done[:, lo:hi] = dn
 
-    lib()
-    if threads <= 1:
-        run(0, B)
-    else:
+    got = lib().mo_set_threads(max(1, int(threads)))
+    if got >= threads or threads <= 1:
+        run(0, B)           # one call, OpenMP splits the environments over the host threads
+    else:                   # library built without OpenMP: python threads, ctypes releases the GIL
         bounds = np.linspace(0, B, threads + 1).astype(int)
         ts = [threading.Thread(target=run, args=(int(bounds[k]), int(bounds[k + 1]))) for k in range(threads)]
         for t in ts:
@@ -222,3 +226,12 @@ def learner_td(q_online, q_target_next, action, reward, done, steps):
     lib().mo_learner_td(n, _p(qo, C.c_float), _p(qt, C.c_float), _p(a, C.c_int64), _p(r, C.c_float),
                         _p(d, C.c_float), _p(s, C.c_float), _p(td, C.c_float), _p(pr, C.c_float))
     return td, pr
+
+
+def comm_mask(pos: np.ndarray, max_comm_agents: int = 3, obs_radius: int = 4) -> np.ndarray:
+    """model.py:196-208 for one environment: pos int[N,2] -> uint8[N,N] (ties -> lower agent id)."""
+    p = np.ascontiguousarray(pos, dtype=np.int32)
+    N = p.shape[0]
+    out = np.empty((N, N), dtype=np.uint8)
+    lib().mo_comm_mask(N, _p(p, C.c_int32), min(max_comm_agents, N), obs_radius, _p(out, C.c_uint8))
+    return out
