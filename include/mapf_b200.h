@@ -181,6 +181,42 @@ int mapf_per_td_update(mapf_per *tree, const float *d_q_online, const float *d_q
 int mapf_actor_td(const float *d_rew, const float *d_q, const uint8_t *d_act, const int32_t *d_size,
                   int32_t episodes, int32_t capacity, double *d_td_out, void *stream);
 
+/* ---- GlobalBuffer.sample_batch window gather (worker.py:106-184) -------------------------------- */
+/* Device-resident replay store in the reference's logical layout (worker.py:36-42): episode slot g owns
+ * observation / comm-mask rows g*(max_steps+1) + f (f = 0..max_steps) and action / reward / hidden rows
+ * g*max_steps + t; sum-tree leaf idx = g*max_steps + t.  All pointers are device memory owned by the caller. */
+typedef struct mapf_replay_view {
+    const uint8_t *obs_buf;    /* u8 bool [(max_steps+1)*capacity, num_agents, 6, 9, 9]   worker.py:36 */
+    const uint8_t *comm_buf;   /* u8 bool [(max_steps+1)*capacity, num_agents, num_agents] worker.py:42 */
+    const uint16_t *hid_buf;   /* fp16 [max_steps*capacity, num_agents, latent_dim]       worker.py:39 */
+    const uint8_t *act_buf;    /* u8  [max_steps*capacity]                                 worker.py:37 */
+    const uint16_t *rew_buf;   /* fp16 [max_steps*capacity]                                worker.py:38 */
+    const uint8_t *done_buf;   /* u8 bool [capacity]                                       worker.py:40 */
+    const int32_t *size_buf;   /* i32 [capacity]                                           worker.py:41 */
+    int32_t num_agents;        /* config.max_num_agetns                                                */
+    int32_t max_steps;         /* config.max_steps (256)                                               */
+    int32_t bt_steps;          /* config.bt_steps (16)                                                 */
+    int32_t forward_steps;     /* config.forward_steps (2)                                             */
+    int32_t latent_dim;        /* config.latent_dim (256)                                              */
+} mapf_replay_view;
+
+/* outputs for `batch` sampled leaves, W = bt_steps + forward_steps frames each (worker.py:168-182) */
+typedef struct mapf_replay_batch {
+    uint16_t *obs;        /* fp16 [batch, W, num_agents, 6, 9, 9], zero padded (worker.py:139-142,169)  */
+    uint8_t *comm_mask;   /* u8 bool [batch, W, num_agents, num_agents]                  (worker.py:176)  */
+    uint16_t *hidden;     /* fp16 [batch*num_agents, latent_dim], zeros while t < bt_steps (worker.py:175) */
+    int64_t *action;      /* i64 [batch]                                                 (worker.py:170)  */
+    uint16_t *reward;     /* fp16 [batch]                                                (worker.py:171)  */
+    uint16_t *done;       /* fp16 [batch] 0 / 1                                          (worker.py:173)  */
+    uint16_t *steps;      /* fp16 [batch] min(forward_steps, size - t)                   (worker.py:174)  */
+    int64_t *bt_steps;    /* i64 [batch] min(t + 1, bt_steps)                            (worker.py:175)  */
+} mapf_replay_batch;
+
+/* d_idx i64[batch]: sampled leaves (from mapf_per_sample).  d_err (optional) i32[1]: bit 0 is set if a
+ * leaf lies beyond its episode's size (the reference asserts, worker.py:120). */
+int mapf_replay_gather(const mapf_replay_view *view, const int64_t *d_idx, int64_t batch, const mapf_replay_batch *out,
+                       int32_t *d_err, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

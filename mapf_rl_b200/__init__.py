@@ -6,7 +6,7 @@ libmapf_b200.so, called through the C ABI in include/mapf_b200.h.  There is no C
 """
 from . import config  # noqa: F401
 
-__all__ = ["config", "BatchedEnvironment", "Environment", "SumTree", "LocalBuffer", "PrioritizedReplayTree"]
+__all__ = ["config", "BatchedEnvironment", "Environment", "SumTree", "LocalBuffer", "PrioritizedReplayTree", "ReplayStore"]
 
 
 def __getattr__(name):
@@ -19,4 +19,7 @@ def __getattr__(name):
     if name in ("SumTree", "LocalBuffer", "PrioritizedReplayTree"):
         from . import buffer
         return getattr(buffer, name)
+    if name == "ReplayStore":
+        from .replay import ReplayStore
+        return ReplayStore
     raise AttributeError(name)

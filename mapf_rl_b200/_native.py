@@ -17,6 +17,18 @@ class EnvConfig(C.Structure):
                 ("obs_radius", C.c_int32), ("device", C.c_int32), ("reward_fn", C.c_float * 5)]
 
 
+class ReplayView(C.Structure):
+    _fields_ = [("obs_buf", C.c_void_p), ("comm_buf", C.c_void_p), ("hid_buf", C.c_void_p), ("act_buf", C.c_void_p),
+                ("rew_buf", C.c_void_p), ("done_buf", C.c_void_p), ("size_buf", C.c_void_p),
+                ("num_agents", C.c_int32), ("max_steps", C.c_int32), ("bt_steps", C.c_int32),
+                ("forward_steps", C.c_int32), ("latent_dim", C.c_int32)]
+
+
+class ReplayBatch(C.Structure):
+    _fields_ = [("obs", C.c_void_p), ("comm_mask", C.c_void_p), ("hidden", C.c_void_p), ("action", C.c_void_p),
+                ("reward", C.c_void_p), ("done", C.c_void_p), ("steps", C.c_void_p), ("bt_steps", C.c_void_p)]
+
+
 # name -> (restype, argtypes); must list every symbol include/mapf_b200.h declares
 _vp, _i32, _i64, _f32, _f64, _u64 = C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.c_double, C.c_uint64
 SIGNATURES = {
@@ -42,6 +54,7 @@ SIGNATURES = {
     "mapf_per_sample": (C.c_int, [_vp, _vp, _i64, _vp, _vp, _vp, _f64, _vp]),
     "mapf_per_td_update": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _f32, _f64, _i64, _i64, _i64,
                                      _vp, _vp, _vp]),
+    "mapf_replay_gather": (C.c_int, [C.POINTER(ReplayView), _vp, _i64, C.POINTER(ReplayBatch), _vp, _vp]),
     "mapf_actor_td": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _vp, _vp]),
 }
 

@@ -8,7 +8,7 @@ import subprocess
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(_HERE, "libmapf_b200.so")
-SOURCES = ["mapf_abi.cu", "mapf_env_kernels.cu", "mapf_step_kernels.cu", "mapf_reset_kernels.cu", "mapf_per_kernels.cu"]
+SOURCES = ["mapf_abi.cu", "mapf_env_kernels.cu", "mapf_step_kernels.cu", "mapf_reset_kernels.cu", "mapf_per_kernels.cu", "mapf_replay_kernels.cu"]
 HEADERS = ["mapf_common.cuh", os.path.join("..", "..", "include", "mapf_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]

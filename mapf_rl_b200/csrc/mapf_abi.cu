@@ -22,6 +22,7 @@ int mapf_launch_per_td_update(mapf_per *, PerScratch *, const float *, const flo
                               const float *, const float *, const float *, const int64_t *, int64_t, float, double, int64_t,
                               int64_t, int64_t, float *, float *, cudaStream_t);
 int mapf_launch_actor_td(const float *, const float *, const uint8_t *, const int32_t *, int, int, double *, cudaStream_t);
+int mapf_launch_replay_gather(const mapf_replay_view *, const int64_t *, int64_t, const mapf_replay_batch *, int32_t *, cudaStream_t);
 
 static thread_local std::string g_last_error;
 
@@ -489,6 +490,33 @@ int mapf_actor_td(const float *d_rew, const float *d_q, const uint8_t *d_act, co
         return MAPF_EINVAL;
     }
     return mapf_launch_actor_td(d_rew, d_q, d_act, d_size, episodes, capacity, d_td_out, static_cast<cudaStream_t>(stream));
+}
+
+int mapf_replay_gather(const mapf_replay_view *view, const int64_t *d_idx, int64_t batch, const mapf_replay_batch *out,
+                       int32_t *d_err, void *stream)
+{
+    if (!view || !out || batch < 0 || (batch > 0 && !d_idx)) {
+        mapf_set_error("mapf_replay_gather: NULL argument");
+        return MAPF_EINVAL;
+    }
+    if (view->num_agents < 1 || view->num_agents > MAPF_MAX_AGENTS || view->max_steps < 1 || view->bt_steps < 1 ||
+        view->forward_steps < 1 || view->latent_dim < 1 || batch > 65535) {
+        mapf_set_error("mapf_replay_gather: bad dimensions (batch <= 65535)");
+        return MAPF_EINVAL;
+    }
+    if (!view->obs_buf || !view->comm_buf || !view->hid_buf || !view->act_buf || !view->rew_buf || !view->done_buf ||
+        !view->size_buf || !out->obs || !out->comm_mask || !out->hidden || !out->action || !out->reward || !out->done ||
+        !out->steps || !out->bt_steps) {
+        mapf_set_error("mapf_replay_gather: NULL buffer");
+        return MAPF_EINVAL;
+    }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        mapf_set_error("mapf_replay_gather: no CUDA device (this library has no CPU fallback)");
+        return MAPF_ECUDA;
+    }
+    if (batch == 0) return MAPF_OK;
+    return mapf_launch_replay_gather(view, d_idx, batch, out, d_err, static_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

@@ -235,3 +235,89 @@ def comm_mask(pos: np.ndarray, max_comm_agents: int = 3, obs_radius: int = 4) ->
     out = np.empty((N, N), dtype=np.uint8)
     lib().mo_comm_mask(N, _p(p, C.c_int32), min(max_comm_agents, N), obs_radius, _p(out, C.c_uint8))
     return out
+
+
+class OracleReplay:
+    """numpy restatement of GlobalBuffer's storage / sampling (worker.py:21-203), with the sum tree of this
+    module and caller-supplied uniforms.  Constants default to config.py:29-30,51,47,65."""
+
+    def __init__(self, capacity, alpha=0.6, beta=0.4, max_num_agents=6, max_steps=256, bt_steps=16, forward_steps=2,
+                 latent_dim=256):
+        self.capacity, self.alpha, self.beta = capacity, alpha, beta
+        self.n, self.S, self.bt, self.fwd, self.latent = max_num_agents, max_steps, bt_steps, forward_steps, latent_dim
+        self.size = 0
+        self.ptr = 0
+        self.priority_tree = OracleSumTree(capacity * max_steps)                                   # :27
+        n, S = self.n, self.S
+        self.obs_buf = np.zeros(((S + 1) * capacity, n, 6, 9, 9), dtype=bool)                      # :36
+        self.act_buf = np.zeros((S * capacity), dtype=np.uint8)
+        self.rew_buf = np.zeros((S * capacity), dtype=np.float16)
+        self.hid_buf = np.zeros((S * capacity, n, latent_dim), dtype=np.float16)
+        self.done_buf = np.zeros(capacity, dtype=bool)
+        self.size_buf = np.zeros(capacity, dtype=np.uint64)
+        self.comm_mask = np.zeros(((S + 1) * capacity, n, n), dtype=bool)                          # :42
+
+    def add(self, buffer_list):  # :68-104
+        S = self.S
+        for buffer in buffer_list:
+            idxes = np.arange(self.ptr * S, (self.ptr + 1) * S, dtype=np.int64)
+            start_idx = self.ptr * S
+            self.size -= int(self.size_buf[self.ptr])
+            self.size += buffer[9]
+            self.priority_tree.batch_update(idxes, np.asarray(buffer[7], dtype=np.float64) ** self.alpha)
+            self.obs_buf[start_idx + self.ptr:start_idx + self.ptr + buffer[9] + 1, :buffer[1]] = buffer[3]
+            self.act_buf[start_idx:start_idx + buffer[9]] = buffer[4]
+            self.rew_buf[start_idx:start_idx + buffer[9]] = buffer[5]
+            self.hid_buf[start_idx:start_idx + buffer[9], :buffer[1]] = buffer[6]
+            self.done_buf[self.ptr] = buffer[8]
+            self.size_buf[self.ptr] = buffer[9]
+            self.comm_mask[start_idx + self.ptr:start_idx + self.ptr + buffer[9] + 1, :buffer[1], :buffer[1]] = buffer[10]
+            self.ptr = (self.ptr + 1) % self.capacity
+
+    def sample_batch(self, batch_size, uniforms):  # :106-184
+        S, bt, fwd = self.S, self.bt, self.fwd
+        b_obs, b_action, b_reward, b_done, b_steps, b_bt_steps, b_comm_mask, b_hidden = [], [], [], [], [], [], [], []
+        idxes, priorities = self.priority_tree.batch_sample(batch_size, uniforms)
+        global_idxes = idxes // S
+        local_idxes = idxes % S
+        for idx, global_idx, local_idx in zip(idxes, global_idxes, local_idxes):
+            idx, global_idx, local_idx = int(idx), int(global_idx), int(local_idx)
+            size = int(self.size_buf[global_idx])
+            assert local_idx < size                                                               # :120
+            steps = int(min(fwd, size - local_idx))                                                # :122
+            if local_idx < bt - 1:                                                                  # :124-127
+                obs = self.obs_buf[global_idx * (S + 1):idx + global_idx + 1 + steps]
+                comm = self.comm_mask[global_idx * (S + 1):idx + global_idx + 1 + steps]
+                hidden = np.zeros((self.n, self.latent), dtype=np.float16)
+            elif local_idx == bt - 1:                                                               # :129-132
+                obs = self.obs_buf[idx + global_idx + 1 - bt:idx + global_idx + 1 + steps]
+                comm = self.comm_mask[global_idx * (S + 1):idx + global_idx + 1 + steps]
+                hidden = np.zeros((self.n, self.latent), dtype=np.float16)
+            else:                                                                                   # :134-137
+                obs = self.obs_buf[idx + global_idx + 1 - bt:idx + global_idx + 1 + steps]
+                comm = self.comm_mask[idx + global_idx + 1 - bt:idx + global_idx + 1 + steps]
+                hidden = self.hid_buf[idx - bt]
+            if obs.shape[0] < bt + fwd:                                                             # :139-142
+                pad_len = bt + fwd - obs.shape[0]
+                obs = np.pad(obs, ((0, pad_len), (0, 0), (0, 0), (0, 0), (0, 0)))
+                comm = np.pad(comm, ((0, pad_len), (0, 0), (0, 0)))
+            done = bool(local_idx == size - 1 and self.done_buf[global_idx])                       # :145-148
+            b_obs.append(obs), b_action.append(self.act_buf[idx]), b_reward.append(self.rew_buf[idx])
+            b_done.append(done), b_steps.append(steps), b_bt_steps.append(min(local_idx + 1, bt))
+            b_comm_mask.append(comm), b_hidden.append(hidden)
+        min_p = np.min(priorities)                                                                  # :165-166
+        weights = np.power(priorities / min_p, -self.beta)
+        return (np.stack(b_obs).astype(np.float16), np.asarray(b_action, dtype=np.int64)[:, None],
+                np.asarray(b_reward, dtype=np.float16)[:, None], np.asarray(b_done, dtype=np.float16)[:, None],
+                np.asarray(b_steps, dtype=np.float16)[:, None], np.asarray(b_bt_steps, dtype=np.int64),
+                np.concatenate(b_hidden), np.stack(b_comm_mask), idxes, weights.astype(np.float16)[:, None], self.ptr)
+
+    def update_priorities(self, idxes, priorities, old_ptr):  # :186-203
+        S = self.S
+        if self.ptr > old_ptr:
+            mask = (idxes < old_ptr * S) | (idxes >= self.ptr * S)
+            idxes, priorities = idxes[mask], priorities[mask]
+        elif self.ptr < old_ptr:
+            mask = (idxes < old_ptr * S) & (idxes >= self.ptr * S)
+            idxes, priorities = idxes[mask], priorities[mask]
+        self.priority_tree.batch_update(np.array(idxes, dtype=np.int64), priorities ** self.alpha)

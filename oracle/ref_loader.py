@@ -18,6 +18,7 @@ Shims (each is the exact old-numpy meaning, nothing else is altered):
 from __future__ import annotations
 
 import importlib
+import importlib.util
 import os
 import sys
 import types
@@ -90,6 +91,40 @@ def load_module(name: str):
         if saved is not None:
             sys.modules[name] = saved
     _cache[key] = mod
+    return mod
+
+
+def load_worker():
+    """Import the reference's worker.py (GlobalBuffer / Learner / Actor) with a no-op `ray` stub: `ray.remote`
+    returns the class unchanged, `ray.put` / `ray.get` are identities.  Only GlobalBuffer's storage / sampling
+    methods are exercised (they do not touch Ray beyond `ray.put` in __init__)."""
+    if "worker" in _cache:
+        return _cache["worker"]
+    if not available():
+        raise RuntimeError(f"reference not mounted at {REFERENCE_DIR}")
+    _install_shims()
+    if "ray" not in sys.modules:
+        ray = types.ModuleType("ray")
+
+        def remote(*a, **k):
+            if a and callable(a[0]) and not k:
+                return a[0]
+            return lambda cls: cls
+        ray.remote, ray.put, ray.get = remote, (lambda x: x), (lambda x: x)
+        sys.modules["ray"] = ray
+    saved = {k: sys.modules.get(k) for k in ("environment", "model", "buffer", "config")}
+    sys.modules["environment"] = load_environment()
+    try:
+        spec = importlib.util.spec_from_file_location("ref_worker", os.path.join(REFERENCE_DIR, "worker.py"))
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+    _cache["worker"] = mod
     return mod
 
 

@@ -251,13 +251,43 @@ def make_per():
     print("per: ok")
 
 
+def make_replay():
+    """GlobalBuffer.add / sample_batch / update_priorities of the live reference (worker.py imported with a no-op
+    ray stub) on the scenario of tests/test_replay.py::drive."""
+    sys.path.insert(0, os.path.abspath(os.path.join(HERE, "..")))
+    from replay_cases import BATCH, CAPACITY
+    from test_replay import drive
+    worker = ref_loader.load_worker()
+
+    def ref_sample(store, seed):
+        np.random.seed(seed)
+        return store.sample_batch(BATCH)
+
+    outs = drive(worker.GlobalBuffer(CAPACITY), ref_sample)
+    out = {}
+    for r, o in enumerate(outs):
+        o = [x.numpy() if hasattr(x, "numpy") else x for x in o]
+        out[f"obs_packed_{r}"] = np.packbits(o[0].astype(bool).reshape(-1))
+        assert set(np.unique(o[0]).tolist()) <= {0.0, 1.0}
+        out[f"action_{r}"], out[f"reward_{r}"], out[f"done_{r}"], out[f"steps_{r}"] = o[1], o[2], o[3], o[4]
+        out[f"bt_steps_{r}"], out[f"hidden_{r}"] = o[5], o[6]
+        out[f"comm_packed_{r}"] = np.packbits(o[7].reshape(-1))
+        out[f"idxes_{r}"], out[f"weights_{r}"], out[f"ptr_{r}"] = np.asarray(o[8], dtype=np.int64), o[9], np.int64(o[10])
+    np.savez_compressed(os.path.join(HERE, "replay.npz"), **out)
+    print("replay: ok")
+
+
 if __name__ == "__main__":
     assert ref_loader.available(), "reference not mounted"
+    if len(sys.argv) > 1 and sys.argv[1] == "replay":
+        make_replay()
+        sys.exit(0)
     make_instances()
     make_crafted()
     make_per()
     make_traces()
     make_navi()
+    make_replay()
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(HERE, f)))
