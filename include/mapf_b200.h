@@ -103,6 +103,13 @@ int mapf_env_step_observe(mapf_env *env, const uint8_t *d_actions, uint8_t *d_ob
 /* Environment.observe (environment.py:433-467).  d_pos (optional) u8[B, N, 2]. */
 int mapf_env_observe(mapf_env *env, uint8_t *d_obs, uint8_t *d_pos, void *stream);
 
+/* Same two calls writing each environment's observation block at its own row of a replay store
+ * (worker.py:96: obs_buf[slot*(max_steps+1) + t]): environment e writes N*486 bytes at
+ * d_obs_base + d_obs_rows[e] * N*486.  d_obs_rows i64[B]. */
+int mapf_env_step_observe_rows(mapf_env *env, const uint8_t *d_actions, uint8_t *d_obs_base, const int64_t *d_obs_rows,
+                               float *d_rewards, uint8_t *d_done, int32_t *d_steps, void *stream);
+int mapf_env_observe_rows(mapf_env *env, uint8_t *d_obs_base, const int64_t *d_obs_rows, uint8_t *d_pos, void *stream);
+
 /* Host-buffer variant of step (what a per-process actor calls): copies actions H2D, runs the fused
  * kernel, copies rewards / done / steps (and obs if h_obs != NULL) D2H, then synchronises.
  * All h_* buffers are ordinary or page-locked host memory; page-locked ones (cudaHostAlloc /

@@ -41,6 +41,8 @@ SIGNATURES = {
     "mapf_env_bfs_navi": (C.c_int, [_vp, _vp, _i32, _vp, _vp]),
     "mapf_env_step_observe": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "mapf_env_observe": (C.c_int, [_vp, _vp, _vp, _vp]),
+    "mapf_env_step_observe_rows": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "mapf_env_observe_rows": (C.c_int, [_vp, _vp, _vp, _vp, _vp]),
     "mapf_env_step_host": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "mapf_env_comm_mask": (C.c_int, [_vp, _i32, _vp, _vp]),
     "mapf_env_get_state": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp]),

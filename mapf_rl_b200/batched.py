@@ -107,10 +107,12 @@ class BatchedEnvironment:
                                                C.c_float(dens), self._stream()))
 
     # -- Environment.step + observe (environment.py:278-467) -------------------------------------
-    def step(self, actions, out_obs=None, out_rewards=None, out_done=None):
+    def step(self, actions, out_obs=None, out_rewards=None, out_done=None, obs_rows=None):
         """actions: uint8 CUDA tensor [B,N] (anything else is converted).
         Returns (obs uint8[B,N,6,9,9], rewards float32[B,N], done uint8[B]); obs is written into
-        `out_obs` when given (e.g. a slot of a device replay tensor)."""
+        `out_obs` when given (e.g. a slot of a device replay tensor).  With `obs_rows` (int64 CUDA tensor [B]),
+        `out_obs` is the whole observation buffer of a replay store ([rows,N,6,9,9]) and environment e writes
+        its block at row obs_rows[e] (returned obs is then `out_obs` itself)."""
         torch = _torch()
         B, N = self.num_envs, self.num_agents
         if not (isinstance(actions, torch.Tensor) and actions.dtype == torch.uint8 and actions.is_cuda
@@ -121,18 +123,30 @@ class BatchedEnvironment:
         obs = out_obs if out_obs is not None else torch.empty((B, N, *self.OBS_SHAPE), dtype=torch.uint8, device=self.device)
         rewards = out_rewards if out_rewards is not None else self._rewards
         done = out_done if out_done is not None else self._done
+        if obs_rows is not None:
+            assert out_obs is not None and obs.is_contiguous() and obs.dtype == torch.uint8 and obs.shape[1] == N
+            assert obs_rows.dtype == torch.int64 and obs_rows.is_cuda and obs_rows.numel() == B
+            _native.check(self._lib.mapf_env_step_observe_rows(
+                self._h, C.c_void_p(actions.data_ptr()), C.c_void_p(obs.data_ptr()), C.c_void_p(obs_rows.data_ptr()),
+                C.c_void_p(rewards.data_ptr()), C.c_void_p(done.data_ptr()), C.c_void_p(self._steps.data_ptr()), self._stream()))
+            return obs, rewards, done
         assert obs.is_contiguous() and obs.dtype == torch.uint8 and obs.numel() == B * N * 486
         _native.check(self._lib.mapf_env_step_observe(self._h, C.c_void_p(actions.data_ptr()), C.c_void_p(obs.data_ptr()),
                                                       C.c_void_p(rewards.data_ptr()), C.c_void_p(done.data_ptr()),
                                                       C.c_void_p(self._steps.data_ptr()), self._stream()))
         return obs, rewards, done
 
-    def observe(self, out_obs=None):
-        """-> (obs uint8[B,N,6,9,9], pos uint8[B,N,2])   (environment.py:433-467)"""
+    def observe(self, out_obs=None, obs_rows=None):
+        """-> (obs uint8[B,N,6,9,9], pos uint8[B,N,2])   (environment.py:433-467); `obs_rows` as in step()."""
         torch = _torch()
         B, N = self.num_envs, self.num_agents
         obs = out_obs if out_obs is not None else torch.empty((B, N, *self.OBS_SHAPE), dtype=torch.uint8, device=self.device)
         pos = torch.empty((B, N, 2), dtype=torch.uint8, device=self.device)
+        if obs_rows is not None:
+            assert out_obs is not None and obs_rows.dtype == torch.int64 and obs_rows.is_cuda and obs_rows.numel() == B
+            _native.check(self._lib.mapf_env_observe_rows(self._h, C.c_void_p(obs.data_ptr()), C.c_void_p(obs_rows.data_ptr()),
+                                                          C.c_void_p(pos.data_ptr()), self._stream()))
+            return obs, pos
         _native.check(self._lib.mapf_env_observe(self._h, C.c_void_p(obs.data_ptr()), C.c_void_p(pos.data_ptr()),
                                                  self._stream()))
         return obs, pos

@@ -11,8 +11,8 @@
 // launchers (other translation units)
 int mapf_launch_pack_load(mapf_env *, const int32_t *, int, const uint8_t *, const uint8_t *, const uint8_t *, cudaStream_t);
 int mapf_launch_bfs(mapf_env *, const int32_t *, int, int32_t *, cudaStream_t);
-int mapf_launch_step(mapf_env *, const uint8_t *, uint8_t *, float *, uint8_t *, int32_t *, cudaStream_t);
-int mapf_launch_observe(mapf_env *, uint8_t *, uint8_t *, cudaStream_t);
+int mapf_launch_step(mapf_env *, const uint8_t *, uint8_t *, const int64_t *, float *, uint8_t *, int32_t *, cudaStream_t);
+int mapf_launch_observe(mapf_env *, uint8_t *, const int64_t *, uint8_t *, cudaStream_t);
 int mapf_launch_unpack(mapf_env *, uint8_t *, uint8_t *, cudaStream_t);
 int mapf_launch_comm_mask(mapf_env *, int, uint8_t *, cudaStream_t);
 int mapf_launch_reset(mapf_env *, const uint8_t *, uint64_t, uint64_t, float, cudaStream_t);
@@ -230,7 +230,29 @@ int mapf_env_step_observe(mapf_env *env, const uint8_t *d_actions, uint8_t *d_ob
         mapf_set_error("mapf_env_step_observe: NULL buffer");
         return MAPF_EINVAL;
     }
-    return mapf_launch_step(env, d_actions, d_obs, d_rewards, d_done, d_steps, static_cast<cudaStream_t>(stream));
+    return mapf_launch_step(env, d_actions, d_obs, nullptr, d_rewards, d_done, d_steps, static_cast<cudaStream_t>(stream));
+}
+
+int mapf_env_step_observe_rows(mapf_env *env, const uint8_t *d_actions, uint8_t *d_obs_base, const int64_t *d_obs_rows,
+                               float *d_rewards, uint8_t *d_done, int32_t *d_steps, void *stream)
+{
+    REQUIRE_ENV(env);
+    if (!d_actions || !d_obs_base || !d_obs_rows || !d_rewards || !d_done) {
+        mapf_set_error("mapf_env_step_observe_rows: NULL buffer");
+        return MAPF_EINVAL;
+    }
+    return mapf_launch_step(env, d_actions, d_obs_base, d_obs_rows, d_rewards, d_done, d_steps,
+                            static_cast<cudaStream_t>(stream));
+}
+
+int mapf_env_observe_rows(mapf_env *env, uint8_t *d_obs_base, const int64_t *d_obs_rows, uint8_t *d_pos, void *stream)
+{
+    REQUIRE_ENV(env);
+    if (!d_obs_base || !d_obs_rows) {
+        mapf_set_error("mapf_env_observe_rows: NULL buffer");
+        return MAPF_EINVAL;
+    }
+    return mapf_launch_observe(env, d_obs_base, d_obs_rows, d_pos, static_cast<cudaStream_t>(stream));
 }
 
 int mapf_env_observe(mapf_env *env, uint8_t *d_obs, uint8_t *d_pos, void *stream)
@@ -240,7 +262,7 @@ int mapf_env_observe(mapf_env *env, uint8_t *d_obs, uint8_t *d_pos, void *stream
         mapf_set_error("mapf_env_observe: NULL buffer");
         return MAPF_EINVAL;
     }
-    return mapf_launch_observe(env, d_obs, d_pos, static_cast<cudaStream_t>(stream));
+    return mapf_launch_observe(env, d_obs, nullptr, d_pos, static_cast<cudaStream_t>(stream));
 }
 
 int mapf_env_step_host(mapf_env *env, const uint8_t *h_actions, uint8_t *h_obs, float *h_rewards, uint8_t *h_done,
@@ -289,7 +311,7 @@ int mapf_env_step_host(mapf_env *env, const uint8_t *h_actions, uint8_t *h_obs, 
     uint8_t *dst_done = out_direct ? h_done : pin_done;
     int32_t *dst_steps = out_direct ? h_steps : pin_steps;
     MAPF_CUDA(cudaMemcpyAsync(env->d_actions, src_act, BN, cudaMemcpyHostToDevice, st));
-    rc = mapf_launch_step(env, env->d_actions, obs_dev, env->d_rewards, env->d_done, env->d_steps_out, st);
+    rc = mapf_launch_step(env, env->d_actions, obs_dev, nullptr, env->d_rewards, env->d_done, env->d_steps_out, st);
     if (rc != MAPF_OK) return rc;
     MAPF_CUDA(cudaMemcpyAsync(dst_rew, env->d_rewards, BN * 4, cudaMemcpyDeviceToHost, st));
     if (dst_steps) MAPF_CUDA(cudaMemcpyAsync(dst_steps, env->d_steps_out, (size_t)d.B * 4, cudaMemcpyDeviceToHost, st));

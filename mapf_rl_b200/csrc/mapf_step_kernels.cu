@@ -28,7 +28,8 @@ struct StepParams {
     int32_t *steps;
     int32_t *err;
     const uint8_t *actions;  // [B,N]           (step only)
-    uint8_t *obs;            // [B,N,6,9,9]
+    uint8_t *obs;            // [B,N,6,9,9], or the base of a replay store when obs_rows is given
+    const int64_t *obs_rows; // optional [B]: env e writes its N*486-byte block at row obs_rows[e] of `obs`
     float *rewards;          // [B,N]           (step only)
     uint8_t *done;           // [B]             (step only)
     int32_t *steps_out;      // [B] optional
@@ -315,7 +316,7 @@ step_observe_kernel(const StepParams p)
         __syncwarp();  // also orders the last s_occ reads before the bit stream overwrites that buffer
 
         const size_t env_bytes = (size_t)N * MAPF_OBS_BYTES_PER_AGENT;
-        uint8_t *obs_env = p.obs + (size_t)e * env_bytes;
+        uint8_t *obs_env = p.obs + (size_t)(p.obs_rows ? p.obs_rows[e] : (int64_t)e) * env_bytes;
         const int head = (int)(reinterpret_cast<uintptr_t>(obs_env) & 15);  // bytes before the 16-B boundary
 
 #pragma unroll
@@ -528,22 +529,24 @@ StepParams make_params(const mapf_env *env)
 
 }  // namespace
 
-int mapf_launch_step(mapf_env *env, const uint8_t *d_actions, uint8_t *d_obs, float *d_rewards, uint8_t *d_done,
-                     int32_t *d_steps, cudaStream_t st)
+int mapf_launch_step(mapf_env *env, const uint8_t *d_actions, uint8_t *d_obs, const int64_t *d_obs_rows, float *d_rewards,
+                     uint8_t *d_done, int32_t *d_steps, cudaStream_t st)
 {
     StepParams p = make_params(env);
     p.actions = d_actions;
     p.obs = d_obs;
+    p.obs_rows = d_obs_rows;
     p.rewards = d_rewards;
     p.done = d_done;
     p.steps_out = d_steps;
     return launch_step<true>(env, p, st);
 }
 
-int mapf_launch_observe(mapf_env *env, uint8_t *d_obs, uint8_t *d_pos, cudaStream_t st)
+int mapf_launch_observe(mapf_env *env, uint8_t *d_obs, const int64_t *d_obs_rows, uint8_t *d_pos, cudaStream_t st)
 {
     StepParams p = make_params(env);
     p.obs = d_obs;
+    p.obs_rows = d_obs_rows;
     p.pos_out = d_pos;
     return launch_step<false>(env, p, st);
 }
