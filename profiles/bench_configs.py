@@ -21,6 +21,7 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 
 def ev_time(torch, fn, iters, warm=5):
@@ -148,6 +149,65 @@ def per_config(torch, out):
                               "finish_256_steps_per_episode": 168, "source": "SURVEY.md section 6 (measured, 1 core)"}})
 
 
+def glue_config(torch, out):
+    """Widened rows: comm-mask kernel, replay window gather (K5), and the whole actor loop (configs[4])."""
+    from bench import measured_hbm_peak
+    from mapf_rl_b200 import BatchedEnvironment, ReplayStore
+    from mapf_rl_b200.actor import BatchedActor
+    from mapf_rl_b200.qnet import Network
+    from replay_cases import make_episode
+    dev = torch.device("cuda", 0)
+    peak, _ = measured_hbm_peak()
+    # comm mask at the bench geometry
+    env = BatchedEnvironment(8192, 32, 40, device=dev)
+    env.reset(seed=0, density=0.3)
+    m = torch.empty((8192, 32, 32), dtype=torch.uint8, device=dev)
+    us = ev_time(torch, lambda: env.comm_mask(out=m), 200)
+    out({"config": "comm mask (model.py:196-208), 8192 envs x 32 agents", "us_per_call": round(us, 2),
+         "agent_rows_per_s": 8192 * 32 / (us * 1e-6), "bytes_written": 8192 * 32 * 32})
+    env.close()
+    # K5 window gather: reference geometry (6 agents, batch 192) and the bench geometry (32 agents)
+    rng = np.random.default_rng(0)
+    for n, cap in ((6, 64), (32, 64)):
+        store = ReplayStore(cap, max_num_agents=n, device=dev)
+        store.add([make_episode(rng, k, n, 256, False) for k in range(cap)])
+        u = torch.rand(192, dtype=torch.float64, device=dev)
+        idx, _, _ = store.priority_tree.sample_device(192, u)
+        us = ev_time(torch, lambda: store.gather(idx), 100)
+        # the torch allocations of gather() are included; bytes: up to 18 frames read as bool, written as fp16
+        W = store.bt_steps + store.forward_steps
+        rd = 192 * W * n * (486 + n) + 192 * n * 256 * 2
+        wr = 192 * W * n * (972 + n) + 192 * n * 256 * 2
+        out({"config": f"K5 replay window gather, batch 192, {n} agents, {W} frames", "us_per_call": round(us, 2),
+             "algorithmic_bytes": rd + wr, "achieved_GBs": (rd + wr) / (us * 1e-6) / 1e9,
+             "roofline_frac_of_measured_hbm": (rd + wr) / (us * 1e-6) / 1e9 / peak})
+        del store
+        torch.cuda.empty_cache()
+    # configs[4]: the actor loop, env batch + Q-net (bf16 autocast) + replay recording
+    B, N, L = 2048, 32, 40
+    env = BatchedEnvironment(B, N, L, device=dev)
+    net = Network().to(dev).eval()
+    store = ReplayStore(2 * B, max_num_agents=N, device=dev)
+    actor = BatchedActor(env, net, store, epsilon=0.1, seed=0, density=0.3)
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        actor.run(3)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        steps = 20
+        actor.run(steps)
+        torch.cuda.synchronize()
+        el = time.perf_counter() - t0
+        obs = torch.zeros((B, N, 6, 9, 9), dtype=torch.uint8, device=dev)
+        comm = env.comm_mask()
+        t_net = ev_time(torch, lambda: net.step(obs, comm), 10, warm=2)
+    t_env = ev_time(torch, lambda: env.step(torch.zeros((B, N), dtype=torch.uint8, device=dev)), 50)
+    out({"config": "C5 actor loop: 2048 envs x 32 agents 40x40, Q-net bf16 autocast, replay recording, auto reset",
+         "ms_per_step": round(el / steps * 1e3, 3), "agent_steps_per_s": B * N * steps / el,
+         "qnet_forward_ms": round(t_net / 1e3, 3), "env_step_observe_us": round(t_env, 2),
+         "episodes_published": actor.episodes, "store_GB": sum(t.numel() * t.element_size() for t in
+                                                                 (store.obs_buf, store.hid_buf, store.comm_mask)) / 1e9})
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "configs.jsonl"))
@@ -173,6 +233,8 @@ def main():
         env_config(torch, out, "C4 80x80/0.3, 64 agents, 4096 envs", 4096, 64, 80, steps=100)
     if not want or "K4" in want:
         per_config(torch, out)
+    if not want or "GLUE" in want:
+        glue_config(torch, out)
     f.close()
 
 
