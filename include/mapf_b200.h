@@ -114,10 +114,26 @@ int mapf_env_observe_rows(mapf_env *env, uint8_t *d_obs_base, const int64_t *d_o
  * kernel, copies rewards / done / steps (and obs if h_obs != NULL) D2H, then synchronises.
  * All h_* buffers are ordinary or page-locked host memory; page-locked ones (cudaHostAlloc /
  * cudaHostRegister / torch pin_memory) are used as DMA endpoints directly, pageable ones are staged through
- * the handle's own pinned area.  d_obs_opt: if non-NULL the observation is written there (device replay
+ * the handle's own pinned area.  By default the kernel stores rewards / done / steps straight into the
+ * page-locked buffers through their device alias (posted PCIe writes that overlap the kernel) instead of
+ * queueing D2H copies behind it; MAPF_STEP_HOST_MODE=0 in the environment selects the DMA path, =2 also
+ * reads the actions in place.  d_obs_opt: if non-NULL the observation is written there (device replay
  * tensor) instead of an internal buffer. */
 int mapf_env_step_host(mapf_env *env, const uint8_t *h_actions, uint8_t *h_obs, float *h_rewards,
                        uint8_t *h_done, int32_t *h_steps, uint8_t *d_obs_opt, void *stream);
+
+/* Diagnostics / tuning (process-wide; profiles/step_variants.py, tests): selects the step kernel form.
+ *   variant     >= 10: split producer/consumer kernel (10 = default shape, 11..17 other warp splits);
+ *               0..3: single-role kernel (CTA shapes);  < 0 leaves the current value
+ *   flags       MAPF_STEPF_* bit set of mapf_step_kernels.cu (1 = L2 evict_last on heuristic-map loads); < 0 keeps
+ *   ctas_per_sm cap on resident CTAs per SM (0 = as many as fit); < 0 keeps
+ * The same three values are read once from MAPF_STEP_VARIANT / MAPF_STEP_FLAGS / MAPF_STEP_CTAS_PER_SM. */
+int mapf_debug_step_tuning(int32_t variant, int32_t flags, int32_t ctas_per_sm);
+/* Diagnosis: while d_trace != NULL (u64[B, 16], device) the split step kernel stamps %globaltimer per environment:
+ * [0] producer reaches the env, [1] its slot is free, [7] inputs loaded, [8] conflicts resolved, [2] step phase
+ * done (state stored), [9] before / [10] after the window gather of agent 0, [3] bit stream published,
+ * [4] consumer reaches the env, [5] stream available, [6] stores issued.  NULL switches it off. */
+int mapf_debug_step_trace(uint64_t *d_trace);
 
 /* ---- communication mask of Network.step (model.py:196-208), the actor-side glue next to observe() ------
  *   d_mask_out u8[B, N, N]: mask[i][j] = 1 iff agent j is inside agent i's 9x9 field of view (|dx| <= 4 and

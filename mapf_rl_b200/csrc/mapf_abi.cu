@@ -13,6 +13,8 @@ int mapf_launch_pack_load(mapf_env *, const int32_t *, int, const uint8_t *, con
 int mapf_launch_bfs(mapf_env *, const int32_t *, int, int32_t *, cudaStream_t);
 int mapf_launch_step(mapf_env *, const uint8_t *, uint8_t *, const int64_t *, float *, uint8_t *, int32_t *, cudaStream_t);
 int mapf_launch_observe(mapf_env *, uint8_t *, const int64_t *, uint8_t *, cudaStream_t);
+void mapf_set_step_tuning(int, int, int);
+void mapf_set_step_trace(unsigned long long *);
 int mapf_launch_unpack(mapf_env *, uint8_t *, uint8_t *, cudaStream_t);
 int mapf_launch_comm_mask(mapf_env *, int, uint8_t *, cudaStream_t);
 int mapf_launch_reset(mapf_env *, const uint8_t *, uint64_t, uint64_t, float, cudaStream_t);
@@ -57,6 +59,31 @@ bool host_is_pinned(const void *p)
         return false;
     }
     return a.type == cudaMemoryTypeHost;
+}
+
+// Device-side alias of a page-locked, mapped host buffer (cudaHostAlloc / torch pin_memory under UVA), or
+// nullptr when the buffer cannot be addressed by a kernel.
+template <typename T>
+T *host_device_alias(T *p)
+{
+    void *dptr = nullptr;
+    if (!p || cudaHostGetDevicePointer(&dptr, const_cast<void *>(static_cast<const void *>(p)), 0) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    return static_cast<T *>(dptr);
+}
+
+// MAPF_STEP_HOST_MODE: 0 = DMA copies either side of the kernel, 1 = the kernel writes rewards / done / steps
+// straight into the caller's page-locked buffers over PCIe (posted writes overlap the kernel; default),
+// 2 = additionally reads the actions from the caller's page-locked buffer.
+int step_host_mode()
+{
+    static const int m = [] {
+        const char *s = std::getenv("MAPF_STEP_HOST_MODE");
+        return s ? std::atoi(s) : 1;
+    }();
+    return m;
 }
 
 template <typename T>
@@ -310,6 +337,25 @@ int mapf_env_step_host(mapf_env *env, const uint8_t *h_actions, uint8_t *h_obs, 
     float *dst_rew = out_direct ? h_rewards : pin_rew;
     uint8_t *dst_done = out_direct ? h_done : pin_done;
     int32_t *dst_steps = out_direct ? h_steps : pin_steps;
+    // zero-copy: the kernel's own stores land in the host buffers (no D2H DMA launches behind the kernel)
+    const int mode = step_host_mode();
+    float *zc_rew = mode >= 1 ? host_device_alias(dst_rew) : nullptr;
+    uint8_t *zc_done = mode >= 1 ? host_device_alias(dst_done) : nullptr;
+    int32_t *zc_steps = mode >= 1 && dst_steps ? host_device_alias(dst_steps) : nullptr;
+    if (zc_rew && zc_done && (zc_steps || !dst_steps)) {
+        const uint8_t *zc_act = mode >= 2 ? host_device_alias(src_act) : nullptr;
+        if (!zc_act) MAPF_CUDA(cudaMemcpyAsync(env->d_actions, src_act, BN, cudaMemcpyHostToDevice, st));
+        rc = mapf_launch_step(env, zc_act ? zc_act : env->d_actions, obs_dev, nullptr, zc_rew, zc_done, zc_steps, st);
+        if (rc != MAPF_OK) return rc;
+        if (h_obs) MAPF_CUDA(cudaMemcpyAsync(h_obs, obs_dev, BN * MAPF_OBS_BYTES_PER_AGENT, cudaMemcpyDeviceToHost, st));
+        MAPF_CUDA(cudaStreamSynchronize(st));
+        if (!out_direct) {
+            std::memcpy(h_rewards, pin_rew, BN * 4);
+            std::memcpy(h_done, pin_done, (size_t)d.B);
+            if (h_steps) std::memcpy(h_steps, pin_steps, (size_t)d.B * 4);
+        }
+        return MAPF_OK;
+    }
     MAPF_CUDA(cudaMemcpyAsync(env->d_actions, src_act, BN, cudaMemcpyHostToDevice, st));
     rc = mapf_launch_step(env, env->d_actions, obs_dev, nullptr, env->d_rewards, env->d_done, env->d_steps_out, st);
     if (rc != MAPF_OK) return rc;
@@ -323,6 +369,18 @@ int mapf_env_step_host(mapf_env *env, const uint8_t *h_actions, uint8_t *h_obs, 
         std::memcpy(h_done, pin_done, (size_t)d.B);
         if (h_steps) std::memcpy(h_steps, pin_steps, (size_t)d.B * 4);
     }
+    return MAPF_OK;
+}
+
+int mapf_debug_step_tuning(int32_t variant, int32_t flags, int32_t ctas_per_sm)
+{
+    mapf_set_step_tuning(variant, flags, ctas_per_sm);
+    return MAPF_OK;
+}
+
+int mapf_debug_step_trace(uint64_t *d_trace)
+{
+    mapf_set_step_trace(reinterpret_cast<unsigned long long *>(d_trace));
     return MAPF_OK;
 }
 

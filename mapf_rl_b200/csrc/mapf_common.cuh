@@ -50,6 +50,7 @@ struct mapf_env {
     uint32_t *navi;
     int32_t *steps;
     int32_t *err;      // latched device error bits
+    int split_key, split_per_sm;  // resident CTAs per SM of the split step kernel, cached per (variant) key
     // staging for the host-buffer entry point
     uint8_t *d_actions;
     uint8_t *d_obs;

@@ -39,6 +39,8 @@ struct StepParams {
     int obst_words;          // = d.obst_stride
     int bits_words;          // words of the per-env observation bit stream (also holds the occupancy grid)
     int flags;               // MAPF_STEPF_*
+    unsigned long long *trace;  // diagnosis: u64[B][16] globaltimer stamps per env (NULL = off), see profiles/step_timeline.py
+    int chunks_per_env;      // split form: N * 486 / 16 16-byte output chunks (= 16-bit stream pieces) per env
 };
 
 enum : int {
@@ -47,11 +49,50 @@ enum : int {
     // diagnosis only (results are WRONG with these set; profiles/step_variants.py uses them to bound the kernel)
     MAPF_STEPF_DIAG_NO_NAVI = 4,   // skip the heuristic-map loads
     MAPF_STEPF_DIAG_NO_STORE = 8,  // skip the observation stores
+    MAPF_STEPF_NO_SPECULATION = 16,  // no speculative L2 prefetch of the heuristic-map line before the step phase
+    MAPF_STEPF_NO_LOOKAHEAD = 32,    // split form: no L2 prefetch of the next environment's inputs
 };
 
 // 4 bits -> 4 bool bytes: bit b lands at bit 8b.  The four shifted copies of x (shifts 0,7,14,21)
 // do not overlap for x < 16, so the multiply has no carries.
 __device__ __forceinline__ uint32_t expand4(uint32_t x) { return (x * 0x00204081u) & 0x01010101u; }
+
+__device__ __forceinline__ uint32_t smem_addr(const void *ptr) { return (uint32_t)__cvta_generic_to_shared(ptr); }
+__device__ __forceinline__ void prefetch_l2(const void *ptr) { asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr)); }
+
+// the warp asks L2 for every 128-byte line of [ptr, ptr + bytes)
+__device__ __forceinline__ void prefetch_span_l2(const void *ptr, size_t bytes, int lane)
+{
+    const uintptr_t lo = reinterpret_cast<uintptr_t>(ptr) & ~(uintptr_t)127;
+    const uintptr_t hi = reinterpret_cast<uintptr_t>(ptr) + bytes;
+    for (uintptr_t q = lo + (uintptr_t)lane * 128; q < hi; q += 32 * 128) prefetch_l2(reinterpret_cast<const void *>(q));
+}
+
+// Inputs of environment e (positions, goals, actions, step counter, obstacle bitmap) -> L2, one env ahead of use.
+__device__ __forceinline__ void prefetch_env_inputs(const StepParams &p, int e, int lane)
+{
+    const size_t N = p.d.N;
+    if (lane < 8) prefetch_span_l2(p.pos + (size_t)e * N * 2, N * 2, lane);
+    else if (lane < 16) prefetch_span_l2(p.goal + (size_t)e * N * 2, N * 2, lane - 8);
+    else if (lane < 20) prefetch_span_l2(p.actions + (size_t)e * N, N, lane - 16);
+    else if (lane == 20) prefetch_l2(p.steps + e);
+    else if (lane >= 24) {
+        // 8 lanes cover the bitmap (576 B at L = 40, 2816 B at L = 120)
+        const uintptr_t base = reinterpret_cast<uintptr_t>(p.obst + (size_t)e * p.d.obst_stride);
+        const uintptr_t hi = base + (size_t)p.d.obst_stride * 4;
+        for (uintptr_t q = (base & ~(uintptr_t)127) + (uintptr_t)(lane - 24) * 128; q < hi; q += 8 * 128)
+            prefetch_l2(reinterpret_cast<const void *>(q));
+    }
+}
+
+__device__ __forceinline__ void trace_stamp(const StepParams &p, int e, int k, int lane)
+{
+    if (p.trace && lane == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        p.trace[(size_t)e * 16 + k] = t;
+    }
+}
 
 __device__ __forceinline__ uint32_t window9(const uint32_t *row, int bitoff)
 {
@@ -104,37 +145,39 @@ struct FieldWalk {
     }
 };
 
-template <int RW, int K, bool DO_STEP, int WARPS, int MINB>
-__global__ void __launch_bounds__(WARPS * 32, MINB)
-step_observe_kernel(const StepParams p)
+// Registers of one environment that outlive env_step_gather (final positions, to clear the agent bitmap).
+template <int K>
+struct EnvRegs {
+    int px[K], py[K];
+    bool valid[K];
+};
+
+// One warp, one environment: Environment.step (DO_STEP) and the observation BIT stream of all its agents.
+// On return the env's N*486-bit stream sits in s_bits starting at bit `head` (every lane has passed a
+// __syncwarp after its last write), positions / rewards / done / steps are stored, and the agent bitmap
+// still holds this env's bits (clear_agent_bits undoes them).
+template <int RW, int K, bool DO_STEP>
+__device__ __forceinline__ void env_step_gather(const StepParams &p, const int e, const int lane, uint32_t *s_obst,
+                                                uint32_t *s_agent, uint32_t *s_bits, uint16_t *s_tgt, uint16_t *s_cell,
+                                                const int head, const uint64_t pol_keep, EnvRegs<K> &out)
 {
     constexpr int RWS = RW + 1;
-    extern __shared__ __align__(16) uint32_t smem[];
     const EnvDims &d = p.d;
-    const int lane = threadIdx.x & 31;
-    const int warp = threadIdx.x >> 5;
     const int N = d.N, L = d.L;
-
-    uint32_t *s_obst = smem + (size_t)warp * p.warp_smem_words;
-    uint32_t *s_agent = s_obst + p.obst_words;
-    uint32_t *s_bits = s_agent + p.obst_words;
-    uint16_t *s_tgt = reinterpret_cast<uint16_t *>(s_bits + p.bits_words);
-    uint16_t *s_cell = s_tgt + 32 * K;
     // The cell -> agent grid of the step phase lives in the bit-stream buffer (the two are never live at
     // the same time).  It is never cleared: an entry is trusted only if it round-trips through s_cell.
     uint8_t *s_occ = reinterpret_cast<uint8_t *>(s_bits);
-
-    const uint64_t pol_keep = l2_policy_evict_last();
-    const uint64_t pol_stream = l2_policy_evict_first();
     const bool navi_keep = p.flags & MAPF_STEPF_NAVI_KEEP;
-    const bool obs_policy = p.flags & MAPF_STEPF_OBS_POLICY;
-
-    // the agent bitmap must start all-zero; afterwards each env clears the bits it set
-    for (int w = lane; w < p.obst_words; w += 32) s_agent[w] = 0;
-    __syncwarp();
-
-    for (int e = blockIdx.x * WARPS + warp; e < d.B; e += gridDim.x * WARPS) {
+    {
         // ---- request every input of this env up front ----
+        {
+            // obstacle bitmap: global -> shared without passing through registers (LDGSTS), so nothing below
+            // waits for it until the cp.async.wait_all in front of the first __syncwarp
+            const uint4 *src = reinterpret_cast<const uint4 *>(p.obst + (size_t)e * d.obst_stride);
+            const uint32_t dst = smem_addr(s_obst);
+            for (int w = lane; w < (p.obst_words >> 2); w += 32)
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 16 * w), "l"(src + w) : "memory");
+        }
         int px[K], py[K];
         bool valid[K];
         [[maybe_unused]] int gx[K], gy[K], act[K];
@@ -159,12 +202,24 @@ step_observe_kernel(const StepParams p)
         }
         if constexpr (DO_STEP)
             if (lane == 0) step_now = p.steps[e];
-        {
-            const uint4 *src = reinterpret_cast<const uint4 *>(p.obst + (size_t)e * d.obst_stride);
-            uint4 *dst = reinterpret_cast<uint4 *>(s_obst);
-            for (int w = lane; w < (p.obst_words >> 2); w += 32) dst[w] = __ldg(src + w);
+        if constexpr (DO_STEP) {
+            // Speculation: the heuristic-map line the observation will need is the tile of the cell the agent moves
+            // to if nothing stops it, or of the cell it is on; ask L2 for it now so that the fetch overlaps the
+            // conflict resolution (the real load follows the committed position and then hits L2).
+            if (!(p.flags & MAPF_STEPF_NO_SPECULATION)) {
+#pragma unroll
+                for (int k = 0; k < K; ++k) {
+                    if (valid[k]) {
+                        const int tx = min(max(px[k] + (act[k] == 2) - (act[k] == 1), 0), L - 1);
+                        const int ty = min(max(py[k] + (act[k] == 4) - (act[k] == 3), 0), L - 1);
+                        const char *base = reinterpret_cast<const char *>(p.navi + ((size_t)e * N + k * 32 + lane) * d.navi_agent_stride);
+                        const int t0 = (px[k] >> 3) * d.NB + (py[k] >> 3), t1 = (tx >> 3) * d.NB + (ty >> 3);
+                        prefetch_l2(base + ((size_t)t1 << 7));
+                        if (t1 != t0) prefetch_l2(base + ((size_t)t0 << 7));
+                    }
+                }
+            }
         }
-
         if constexpr (DO_STEP) {
             int tx[K], ty[K], tcell[K], mycell[K], occ_j[K];
             float rew[K];
@@ -180,7 +235,9 @@ step_observe_kernel(const StepParams p)
                 s_cell[a] = valid[k] ? (uint16_t)mycell[k] : (uint16_t)0xffff;
                 if (valid[k]) s_occ[mycell[k]] = (uint8_t)a;
             }
+            asm volatile("cp.async.wait_all;" ::: "memory");
             __syncwarp();  // staged obstacle bitmap, s_cell and s_occ visible to every lane
+            trace_stamp(p, e, 7, lane);
 #pragma unroll
             for (int k = 0; k < K; ++k) {
                 // stay / move pass, environment.py:298-311
@@ -269,6 +326,7 @@ step_observe_kernel(const StepParams p)
                 }
                 if (!__any_sync(MAPF_FULL_MASK, changed)) break;
             }
+            trace_stamp(p, e, 8, lane);
             // commit, environment.py:410-421
             bool all_goal = true;
 #pragma unroll
@@ -305,19 +363,17 @@ step_observe_kernel(const StepParams p)
                         reinterpret_cast<uchar2 *>(p.pos_out)[(size_t)e * N + k * 32 + lane] =
                             make_uchar2((unsigned char)px[k], (unsigned char)py[k]);
             }
+            asm volatile("cp.async.wait_all;" ::: "memory");
             __syncwarp();  // s_obst visible
         }
 
+        trace_stamp(p, e, 2, lane);
         // ---------------- observe, environment.py:433-467 ----------------
         // agent bitmap (environment.py:449-451): one shared-memory atomic per agent
 #pragma unroll
         for (int k = 0; k < K; ++k)
             if (valid[k]) atomicOr(&s_agent[(px[k] + 4) * RWS + ((py[k] + 4) >> 5)], 1u << ((py[k] + 4) & 31));
         __syncwarp();  // also orders the last s_occ reads before the bit stream overwrites that buffer
-
-        const size_t env_bytes = (size_t)N * MAPF_OBS_BYTES_PER_AGENT;
-        uint8_t *obs_env = p.obs + (size_t)(p.obs_rows ? p.obs_rows[e] : (int64_t)e) * env_bytes;
-        const int head = (int)(reinterpret_cast<uintptr_t>(obs_env) & 15);  // bytes before the 16-B boundary
 
 #pragma unroll
         for (int k = 0; k < K; ++k) {
@@ -368,7 +424,9 @@ step_observe_kernel(const StepParams p)
                     else S[m] = __funnelshift_l(prev, w, o);
                     prev = w;
                 };
+                if (k == 0) trace_stamp(p, e, 9, lane);
                 FieldWalk<0>::run(0ull, val, emit);
+                if (k == 0) trace_stamp(p, e, 10, lane);
                 if (((o + 485) >> 5) == 16) S[16] = __funnelshift_l(prev, 0u, o);
             }
             __syncwarp();
@@ -379,6 +437,58 @@ step_observe_kernel(const StepParams p)
             }
             __syncwarp();
         }
+
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            out.px[k] = px[k];
+            out.py[k] = py[k];
+            out.valid[k] = valid[k];
+        }
+    }
+}
+
+template <int RW, int K>
+__device__ __forceinline__ void clear_agent_bits(uint32_t *s_agent, const EnvRegs<K> &r)
+{
+    constexpr int RWS = RW + 1;
+#pragma unroll
+    for (int k = 0; k < K; ++k)
+        if (r.valid[k]) s_agent[(r.px[k] + 4) * RWS + ((r.py[k] + 4) >> 5)] = 0;
+    __syncwarp();
+}
+
+// ---- K1+K2, single-role form: every warp steps an env, then expands and stores its own observation block.
+// Kept for observe(), unaligned observation bases and agent counts that are not a multiple of 8.
+template <int RW, int K, bool DO_STEP, int WARPS, int MINB>
+__global__ void __launch_bounds__(WARPS * 32, MINB)
+step_observe_kernel(const StepParams p)
+{
+    extern __shared__ __align__(16) uint32_t smem[];
+    const EnvDims &d = p.d;
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int N = d.N;
+
+    uint32_t *s_obst = smem + (size_t)warp * p.warp_smem_words;
+    uint32_t *s_agent = s_obst + p.obst_words;
+    uint32_t *s_bits = s_agent + p.obst_words;
+    uint16_t *s_tgt = reinterpret_cast<uint16_t *>(s_bits + p.bits_words);
+    uint16_t *s_cell = s_tgt + 32 * K;
+
+    const uint64_t pol_keep = l2_policy_evict_last();
+    const uint64_t pol_stream = l2_policy_evict_first();
+    const bool obs_policy = p.flags & MAPF_STEPF_OBS_POLICY;
+
+    // the agent bitmap must start all-zero; afterwards each env clears the bits it set
+    for (int w = lane; w < p.obst_words; w += 32) s_agent[w] = 0;
+    __syncwarp();
+
+    for (int e = blockIdx.x * WARPS + warp; e < d.B; e += gridDim.x * WARPS) {
+        const size_t env_bytes = (size_t)N * MAPF_OBS_BYTES_PER_AGENT;
+        uint8_t *obs_env = p.obs + (size_t)(p.obs_rows ? p.obs_rows[e] : (int64_t)e) * env_bytes;
+        const int head = (int)(reinterpret_cast<uintptr_t>(obs_env) & 15);  // bytes before the 16-B boundary
+        EnvRegs<K> r;
+        env_step_gather<RW, K, DO_STEP>(p, e, lane, s_obst, s_agent, s_bits, s_tgt, s_cell, head, pol_keep, r);
 
         // expand 1 bit -> 1 bool byte, 16 bytes per lane per store, fully coalesced streaming stores
         {
@@ -411,11 +521,119 @@ step_observe_kernel(const StepParams p)
             }
         }
         __syncwarp();
-        // clear the agent bits this env set
-#pragma unroll
-        for (int k = 0; k < K; ++k)
-            if (valid[k]) s_agent[(px[k] + 4) * RWS + ((py[k] + 4) >> 5)] = 0;
+        clear_agent_bits<RW, K>(s_agent, r);  // the agent bits this env set
+    }
+}
+
+// ---- K1+K2, split form (the hot path) -----------------------------------------------------------------
+// The single-role kernel keeps every warp in lockstep: all of them compute (DRAM idle), then all of them
+// store (issue slots idle), because equal sharing of the DRAM bandwidth keeps their phases aligned.  Here the
+// two halves are different warps of one CTA, decoupled by a shared-memory ring:
+//   * P producer warps run env_step_gather; each owns two slots and leaves the env's 486*N-BIT stream
+//     (1944 B at N = 32) in one of them, then arrives on the slot's `full` mbarrier;
+//   * C consumer warps visit the slots in the producers' (static) order; for each they expand the stream to
+//     bool bytes, 16 B per lane, and write the env's block together (adjacent 512-byte pieces, streaming
+//     stores), then arrive on the slot's `empty` mbarrier.
+// Producers never wait on DRAM (only on a free slot), so stepping env i+1 overlaps the stores of env i, and a
+// CTA emits one contiguous 15.5-KB block at a time instead of P interleaved ones.
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_addr(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "MAPF_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra MAPF_DONE;\n"
+        "bra MAPF_WAIT;\n"
+        "MAPF_DONE:\n"
+        "}" ::"r"(smem_addr(bar)),
+        "r"(parity)
+        : "memory");
+}
+
+template <int RW, int K, int P, int C>
+__global__ void __launch_bounds__((P + C) * 32, K == 1 ? 1536 / ((P + C) * 32) : 1)
+step_split_kernel(const StepParams p)
+{
+    extern __shared__ __align__(16) uint32_t smem[];
+    const EnvDims &d = p.d;
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    // barriers: full[w][s] at bars[2 (2 w + s)], empty[w][s] right behind it
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem);
+    uint32_t *work = smem + ((4 * P * 2 + 3) & ~3);
+    if (threadIdx.x < 2 * P) {
+        mbar_init(bars + 2 * threadIdx.x, 1);      // full: the producer's lane 0
+        mbar_init(bars + 2 * threadIdx.x + 1, C);  // empty: lane 0 of every consumer warp
+    }
+    __syncthreads();
+    const int slot_words = p.bits_words;
+    const int estride = gridDim.x * P;
+
+    if (warp < P) {
+        // ---------------- producer ----------------
+        uint32_t *s_obst = work + (size_t)warp * p.warp_smem_words;
+        uint32_t *s_agent = s_obst + p.obst_words;
+        uint16_t *s_tgt = reinterpret_cast<uint16_t *>(s_agent + p.obst_words);
+        uint16_t *s_cell = s_tgt + 32 * K;
+        uint32_t *slots = reinterpret_cast<uint32_t *>(s_cell + 32 * K);
+        const uint64_t pol_keep = l2_policy_evict_last();
+        for (int w = lane; w < p.obst_words; w += 32) s_agent[w] = 0;
         __syncwarp();
+        int it = 0;
+        for (int e = blockIdx.x * P + warp; e < d.B; e += estride, ++it) {
+            const int s = it & 1;
+            trace_stamp(p, e, 0, lane);
+            if (e + estride < d.B && !(p.flags & MAPF_STEPF_NO_LOOKAHEAD)) prefetch_env_inputs(p, e + estride, lane);
+            mbar_wait(bars + 2 * (2 * warp + s) + 1, ((it >> 1) & 1) ^ 1);  // slot free (first use: passes)
+            trace_stamp(p, e, 1, lane);
+            EnvRegs<K> r;
+            env_step_gather<RW, K, true>(p, e, lane, s_obst, s_agent, slots + s * slot_words, s_tgt, s_cell, 0, pol_keep, r);
+            if (lane == 0) mbar_arrive(bars + 2 * (2 * warp + s));  // every lane's writes precede the last __syncwarp
+            trace_stamp(p, e, 3, lane);
+            clear_agent_bits<RW, K>(s_agent, r);
+        }
+    } else {
+        // ---------------- consumer ----------------
+        const int cw = warp - P;
+        const int cpe = p.chunks_per_env;
+        const size_t env_bytes = (size_t)d.N * MAPF_OBS_BYTES_PER_AGENT;
+        for (int r = 0, e0 = blockIdx.x * P; e0 < d.B; ++r, e0 += estride) {
+            const int s = r & 1;
+#pragma unroll 1
+            for (int w = 0; w < P; ++w) {
+                const int e = e0 + w;
+                if (e >= d.B) break;
+                const int64_t row = p.obs_rows ? __ldg(p.obs_rows + e) : (int64_t)e;
+                uint4 *dst = reinterpret_cast<uint4 *>(p.obs + (size_t)row * env_bytes);
+                const uint16_t *S16 = reinterpret_cast<const uint16_t *>(work + (size_t)w * p.warp_smem_words + 2 * p.obst_words +
+                                                                         32 * K + s * slot_words);
+                if (cw == 0) trace_stamp(p, e, 4, lane);
+                mbar_wait(bars + 2 * (2 * w + s), (r >> 1) & 1);
+                if (cw == 0) trace_stamp(p, e, 5, lane);
+#pragma unroll 4
+                for (int c = cw * 32 + lane; c < cpe; c += C * 32) {
+                    const uint32_t x = S16[c];
+                    uint4 v;
+                    v.x = expand4(x & 0xfu);
+                    v.y = expand4((x >> 4) & 0xfu);
+                    v.z = expand4((x >> 8) & 0xfu);
+                    v.w = expand4(x >> 12);
+                    __stcs(dst + c, v);
+                }
+                __syncwarp();
+                if (cw == 0) trace_stamp(p, e, 6, lane);
+                if (lane == 0) mbar_arrive(bars + 2 * (2 * w + s) + 1);
+            }
+        }
     }
 }
 
@@ -424,11 +642,12 @@ struct StepTuning {
     int variant;       // CTA shape / register cap of the (RW = 2, K = 1) instantiation, see launch_step_rwk
     int flags;
     int ctas_per_sm;   // > 0: persistent grid of that many CTAs per SM, each warp strides over environments
+    unsigned long long *trace = nullptr;
 };
 
-const StepTuning &tuning()
+StepTuning &tuning()
 {
-    static const StepTuning t = [] {
+    static StepTuning t = [] {
         StepTuning r{1, MAPF_STEPF_NAVI_KEEP, 0};
         if (const char *s = std::getenv("MAPF_STEP_VARIANT")) r.variant = std::atoi(s);
         if (const char *s = std::getenv("MAPF_STEP_FLAGS")) r.flags = std::atoi(s);
@@ -457,6 +676,80 @@ int launch_step_cfg(const mapf_env *env, StepParams &p, cudaStream_t st)
     kern<<<grid, WARPS * 32, smem, st>>>(p);
     MAPF_CUDA(cudaGetLastError());
     return MAPF_OK;
+}
+
+// Split form: one CTA serves P environments per round; the grid is persistent (a few CTAs per SM) so that
+// the slot ring stays warm, but nothing requires the CTAs to be co-resident.
+template <int RW, int K, int P, int C>
+int launch_split_cfg(mapf_env *env, StepParams p, cudaStream_t st)
+{
+    auto kern = step_split_kernel<RW, K, P, C>;
+    const EnvDims &d = env->d;
+    // per producer: obstacle + agent bitmaps, s_tgt + s_cell, two slots (bit stream / occupancy grid)
+    const int stream_words = (((d.N * MAPF_OBS_BYTES_PER_AGENT + 31) >> 5) + 2 + 3) & ~3;
+    const int occ_words = (((d.L * d.L + 3) >> 2) + 3) & ~3;
+    p.bits_words = stream_words > occ_words ? stream_words : occ_words;
+    p.warp_smem_words = 2 * p.obst_words + 32 * d.K + 2 * p.bits_words;
+    const size_t smem = ((size_t)((4 * P * 2 + 3) & ~3) + (size_t)p.warp_smem_words * P) * 4;
+    if (smem > 227 * 1024) return MAPF_EINVAL;  // caller falls back to the single-role kernel
+    const int key = 1 + P * 64 + C;
+    if (env->split_key != key) {
+        int per_sm = 0;
+        MAPF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        MAPF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, (P + C) * 32, smem));
+        env->split_per_sm = per_sm < 1 ? 1 : per_sm;
+        env->split_key = key;
+    }
+    int ctas = env->split_per_sm;
+    if (tuning().ctas_per_sm > 0 && ctas > tuning().ctas_per_sm) ctas = tuning().ctas_per_sm;
+    int grid = env->num_sms * ctas;
+    const int want = (d.B + P - 1) / P;
+    if (grid > want) grid = want;
+    kern<<<grid, (P + C) * 32, smem, st>>>(p);
+    MAPF_CUDA(cudaGetLastError());
+    return MAPF_OK;
+}
+
+template <int RW, int K>
+int launch_split_rwk(mapf_env *env, const StepParams &p, cudaStream_t st)
+{
+    if constexpr (RW == 2 && K == 1) {
+        switch (tuning().variant) {
+            case 11: return launch_split_cfg<RW, K, 4, 4>(env, p, st);
+            case 12: return launch_split_cfg<RW, K, 6, 2>(env, p, st);
+            case 13: return launch_split_cfg<RW, K, 7, 5>(env, p, st);
+            case 14: return launch_split_cfg<RW, K, 3, 1>(env, p, st);
+            case 15: return launch_split_cfg<RW, K, 4, 2>(env, p, st);
+            case 16: return launch_split_cfg<RW, K, 2, 2>(env, p, st);
+            case 17: return launch_split_cfg<RW, K, 3, 3>(env, p, st);
+            case 18: return launch_split_cfg<RW, K, 8, 4>(env, p, st);
+            case 19: return launch_split_cfg<RW, K, 10, 6>(env, p, st);
+            default: break;
+        }
+    }
+    return launch_split_cfg<RW, K, 5, 3>(env, p, st);
+}
+
+int launch_split(mapf_env *env, const StepParams &p, cudaStream_t st)
+{
+    const int key = env->d.RW * 10 + env->d.K;
+    switch (key) {
+        case 11: return launch_split_rwk<1, 1>(env, p, st);
+        case 12: return launch_split_rwk<1, 2>(env, p, st);
+        case 21: return launch_split_rwk<2, 1>(env, p, st);
+        case 22: return launch_split_rwk<2, 2>(env, p, st);
+        case 23: return launch_split_rwk<2, 3>(env, p, st);
+        case 24: return launch_split_rwk<2, 4>(env, p, st);
+        case 31: return launch_split_rwk<3, 1>(env, p, st);
+        case 32: return launch_split_rwk<3, 2>(env, p, st);
+        case 33: return launch_split_rwk<3, 3>(env, p, st);
+        case 34: return launch_split_rwk<3, 4>(env, p, st);
+        case 41: return launch_split_rwk<4, 1>(env, p, st);
+        case 42: return launch_split_rwk<4, 2>(env, p, st);
+        case 43: return launch_split_rwk<4, 3>(env, p, st);
+        case 44: return launch_split_rwk<4, 4>(env, p, st);
+    }
+    return MAPF_EINVAL;  // caller falls back to the single-role kernel
 }
 
 template <int RW, int K, bool DO_STEP>
@@ -524,10 +817,22 @@ StepParams make_params(const mapf_env *env)
     const int words = 2 * p.obst_words + p.bits_words + (32 * d.K) /* s_tgt + s_cell, u16 each */;
     p.warp_smem_words = (words + 3) & ~3;
     p.flags = tuning().flags;
+    p.trace = tuning().trace;
+    p.chunks_per_env = d.N * MAPF_OBS_BYTES_PER_AGENT / 16;
     return p;
 }
 
 }  // namespace
+
+void mapf_set_step_tuning(int variant, int flags, int ctas_per_sm)
+{
+    StepTuning &t = tuning();
+    if (variant >= 0) t.variant = variant;
+    if (flags >= 0) t.flags = flags;
+    if (ctas_per_sm >= 0) t.ctas_per_sm = ctas_per_sm;
+}
+
+void mapf_set_step_trace(unsigned long long *d_trace) { tuning().trace = d_trace; }
 
 int mapf_launch_step(mapf_env *env, const uint8_t *d_actions, uint8_t *d_obs, const int64_t *d_obs_rows, float *d_rewards,
                      uint8_t *d_done, int32_t *d_steps, cudaStream_t st)
@@ -539,6 +844,13 @@ int mapf_launch_step(mapf_env *env, const uint8_t *d_actions, uint8_t *d_obs, co
     p.rewards = d_rewards;
     p.done = d_done;
     p.steps_out = d_steps;
+    // the split (producer / consumer) kernel is the hot path; variant 0..3 select the single-role kernel
+    const bool aligned = (reinterpret_cast<uintptr_t>(d_obs) & 15) == 0;
+    const bool diag = p.flags & (MAPF_STEPF_DIAG_NO_NAVI | MAPF_STEPF_DIAG_NO_STORE | MAPF_STEPF_OBS_POLICY);
+    if (env->d.N % 8 == 0 && aligned && !diag && tuning().variant >= 10) {
+        const int rc = launch_split(env, p, st);
+        if (rc != MAPF_EINVAL) return rc;
+    }
     return launch_step<true>(env, p, st);
 }
 

@@ -101,7 +101,7 @@ def main():
             env["MAPF_STEP_CTAS_PER_SM"] = parts[2]
         cmd = [sys.executable, os.path.abspath(__file__), "--child", "--envs", str(args.envs), "--agents", str(args.agents),
                "--side", str(args.side), "--steps", str(args.steps)]
-        r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=600)
+        r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=180)
         out = [l for l in r.stdout.splitlines() if l.startswith("{")]
         print(out[-1] if out else f"variant {spec} FAILED rc={r.returncode}: {r.stderr[-600:]}", flush=True)
 
