@@ -259,22 +259,7 @@ def run_ours(args):
     e2e_run(1, True)
     e2e_obs_value = e2e_run(max(3, min(args.steps, 20)), True)
 
-    # context for the roofline: what a write-only stream of the same size reaches on this GPU
-    def write_probe():
-        buf = replay.view(-1)
-        for _ in range(3):
-            buf.zero_()
-        torch.cuda.synchronize(dev)
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(10):
-            buf.zero_()
-        e1.record()
-        torch.cuda.synchronize(dev)
-        return buf.numel() * 10 / (e0.elapsed_time(e1) * 1e-3) / 1e9
-
     line = None
-    probe = write_probe()
     if rank == 0:
         peak, peak_src = measured_hbm_peak()
         per_launch_s = ms * 1e-3 / args.steps
@@ -298,17 +283,17 @@ def run_ours(args):
             "clocks": clocks,
             "gpu_launches": args.steps,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * N, "d2h_bytes_per_step": B * N * 4 + B * 5,
-                    "api": "mapf_env_step_host: host actions -> H2D -> fused kernel -> D2H rewards/done/steps; "
-                           "observations stay in the device replay ring (north star)", "steps": e2e_steps},
+                    "api": "mapf_env_step_host: pinned host actions -> fused kernel, which reads the actions from and stores rewards/done/steps "
+                           "straight into the pinned host buffers over PCIe (zero-copy) -> sync; observations stay in the device "
+                           "replay ring (north star)", "steps": e2e_steps, "host_mode": os.environ.get("MAPF_STEP_HOST_MODE", "2")},
             "e2e_host_obs": {"value": e2e_obs_value, "unit": UNIT, "h2d_bytes_per_step": B * N,
                              "d2h_bytes_per_step": B * N * 4 + B * 5 + B * N * 486,
                              "api": "same call with the full observation tensor also copied to host (drop-in Environment.step)"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "kernel": "step_observe_kernel<RW=2,K=1,DO_STEP,4 warps,12 CTAs/SM>",
                          "algorithmic_bytes_per_agent_step": algo_bytes(N, L), "peak_source": peak_src,
-                         "write_only_probe_GBs": probe,
-                         "note": "peak = measured copy (read+write) bandwidth; write_only_probe_GBs = torch zero_() over the "
-                                 "observation ring on this GPU, the ceiling of a write-dominated kernel"},
+                         "note": "peak = measured copy (read+write) bandwidth; what plain write / mixed streams of this "
+                                 "shape reach on a B200 is in profiles/r1_membw_probe.jsonl"},
         }
         if not args.no_cpu_baseline and world == 1:
             S = min(2048, B)

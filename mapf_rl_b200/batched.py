@@ -172,11 +172,18 @@ class BatchedEnvironment:
                       done=torch.empty((B,), dtype=torch.uint8, pin_memory=True),
                       steps=torch.empty((B,), dtype=torch.int32, pin_memory=True))
             hb.update({k + "_np": v.numpy() for k, v in list(hb.items())})
+            hb["ptrs"] = tuple(C.c_void_p(hb[k].data_ptr()) for k in ("actions", "rewards", "done", "steps"))
             self._hb = hb
         if want_obs and "obs" not in hb:
             hb["obs"] = torch.empty((B, N, *self.OBS_SHAPE), dtype=torch.uint8, pin_memory=True)
             hb["obs_np"] = hb["obs"].numpy()
         return hb
+
+    @property
+    def host_actions(self) -> np.ndarray:
+        """uint8[B,N] page-locked action buffer of step_host; fill it in place and pass it to step_host to skip
+        the staging copy."""
+        return self._host_buffers(False)["actions_np"]
 
     def step_host(self, actions: np.ndarray, want_obs: bool = False, device_obs=None):
         """Host-buffer step through mapf_env_step_host: numpy in, numpy out, synchronous.
@@ -184,12 +191,13 @@ class BatchedEnvironment:
         they are overwritten by the next step_host call (copy them to keep them)."""
         B, N = self.num_envs, self.num_agents
         hb = self._host_buffers(want_obs)
-        a = np.asarray(actions)
-        assert a.shape == (B, N), "actions number"
-        np.copyto(hb["actions_np"], a, casting="unsafe")
+        if actions is not hb["actions_np"]:   # the caller may fill env.host_actions in place instead
+            a = np.asarray(actions)
+            assert a.shape == (B, N), "actions number"
+            np.copyto(hb["actions_np"], a, casting="unsafe")
+        pa, pr, pd, ps = hb["ptrs"]
         _native.check(self._lib.mapf_env_step_host(
-            self._h, hb["actions"].data_ptr(), hb["obs"].data_ptr() if want_obs else None,
-            hb["rewards"].data_ptr(), hb["done"].data_ptr(), hb["steps"].data_ptr(),
+            self._h, pa, hb["obs"].data_ptr() if want_obs else None, pr, pd, ps,
             C.c_void_p(device_obs.data_ptr()) if device_obs is not None else None, self._stream()))
         return (hb["obs_np"] if want_obs else None), hb["rewards_np"], hb["done_np"], hb["steps_np"]
 

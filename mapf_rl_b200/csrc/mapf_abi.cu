@@ -75,13 +75,13 @@ T *host_device_alias(T *p)
 }
 
 // MAPF_STEP_HOST_MODE: 0 = DMA copies either side of the kernel, 1 = the kernel writes rewards / done / steps
-// straight into the caller's page-locked buffers over PCIe (posted writes overlap the kernel; default),
-// 2 = additionally reads the actions from the caller's page-locked buffer.
+// straight into the caller's page-locked buffers over PCIe (posted writes overlap the kernel),
+// 2 = additionally reads the actions from the caller's page-locked buffer (default).
 int step_host_mode()
 {
     static const int m = [] {
         const char *s = std::getenv("MAPF_STEP_HOST_MODE");
-        return s ? std::atoi(s) : 1;
+        return s ? std::atoi(s) : 2;
     }();
     return m;
 }
@@ -327,8 +327,16 @@ int mapf_env_step_host(mapf_env *env, const uint8_t *h_actions, uint8_t *h_obs, 
     uint8_t *pin_done = reinterpret_cast<uint8_t *>(pin_steps + d.B);
     // page-locked caller buffers are used as DMA endpoints directly; pageable ones go through the handle's
     // pinned staging area (one extra host memcpy each way)
-    const bool act_direct = host_is_pinned(h_actions);
-    const bool out_direct = host_is_pinned(h_rewards) && host_is_pinned(h_done) && (!h_steps || host_is_pinned(h_steps));
+    const void *keys[4] = {h_actions, h_rewards, h_done, h_steps};
+    for (int i = 0; i < 4; ++i) {
+        if (keys[i] != env->hc_key[i]) {
+            env->hc_key[i] = keys[i];
+            env->hc_pinned[i] = keys[i] && host_is_pinned(keys[i]);
+            env->hc_alias[i] = env->hc_pinned[i] ? host_device_alias(const_cast<void *>(keys[i])) : nullptr;
+        }
+    }
+    const bool act_direct = env->hc_pinned[0];
+    const bool out_direct = env->hc_pinned[1] && env->hc_pinned[2] && (!h_steps || env->hc_pinned[3]);
     const uint8_t *src_act = h_actions;
     if (!act_direct) {
         std::memcpy(pin_act, h_actions, BN);
@@ -337,15 +345,33 @@ int mapf_env_step_host(mapf_env *env, const uint8_t *h_actions, uint8_t *h_obs, 
     float *dst_rew = out_direct ? h_rewards : pin_rew;
     uint8_t *dst_done = out_direct ? h_done : pin_done;
     int32_t *dst_steps = out_direct ? h_steps : pin_steps;
-    // zero-copy: the kernel's own stores land in the host buffers (no D2H DMA launches behind the kernel)
+    // zero-copy: the kernel's own loads / stores reach the host buffers (no DMA launches around the kernel)
     const int mode = step_host_mode();
-    float *zc_rew = mode >= 1 ? host_device_alias(dst_rew) : nullptr;
-    uint8_t *zc_done = mode >= 1 ? host_device_alias(dst_done) : nullptr;
-    int32_t *zc_steps = mode >= 1 && dst_steps ? host_device_alias(dst_steps) : nullptr;
+    float *zc_rew = nullptr;
+    uint8_t *zc_done = nullptr;
+    int32_t *zc_steps = nullptr;
+    const uint8_t *zc_act = nullptr;
+    if (mode >= 1) {
+        if (out_direct) {
+            zc_rew = static_cast<float *>(env->hc_alias[1]);
+            zc_done = static_cast<uint8_t *>(env->hc_alias[2]);
+            zc_steps = static_cast<int32_t *>(env->hc_alias[3]);
+        } else {
+            if (!env->pin_alias) env->pin_alias = host_device_alias(env->h_pinned);
+            if (env->pin_alias) {
+                zc_rew = reinterpret_cast<float *>(env->pin_alias + (reinterpret_cast<uint8_t *>(pin_rew) - env->h_pinned));
+                zc_done = env->pin_alias + (pin_done - env->h_pinned);
+                zc_steps = reinterpret_cast<int32_t *>(env->pin_alias + (reinterpret_cast<uint8_t *>(pin_steps) - env->h_pinned));
+            }
+        }
+        if (mode >= 2) {
+            if (act_direct) zc_act = static_cast<const uint8_t *>(env->hc_alias[0]);
+            else if (env->pin_alias) zc_act = env->pin_alias;
+        }
+    }
     if (zc_rew && zc_done && (zc_steps || !dst_steps)) {
-        const uint8_t *zc_act = mode >= 2 ? host_device_alias(src_act) : nullptr;
         if (!zc_act) MAPF_CUDA(cudaMemcpyAsync(env->d_actions, src_act, BN, cudaMemcpyHostToDevice, st));
-        rc = mapf_launch_step(env, zc_act ? zc_act : env->d_actions, obs_dev, nullptr, zc_rew, zc_done, zc_steps, st);
+        rc = mapf_launch_step(env, zc_act ? zc_act : env->d_actions, obs_dev, nullptr, zc_rew, zc_done, dst_steps ? zc_steps : nullptr, st);
         if (rc != MAPF_OK) return rc;
         if (h_obs) MAPF_CUDA(cudaMemcpyAsync(h_obs, obs_dev, BN * MAPF_OBS_BYTES_PER_AGENT, cudaMemcpyDeviceToHost, st));
         MAPF_CUDA(cudaStreamSynchronize(st));

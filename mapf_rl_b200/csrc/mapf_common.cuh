@@ -58,6 +58,12 @@ struct mapf_env {
     uint8_t *d_done;
     int32_t *d_steps_out;
     uint8_t *h_pinned;  // pinned staging: actions | rewards | done | steps
+    // last caller buffers of mapf_env_step_host and what they resolved to (a per-step actor reuses its buffers, so
+    // the four cudaPointerGetAttributes / cudaHostGetDevicePointer queries are paid once)
+    uint8_t *pin_alias;  // device alias of h_pinned
+    const void *hc_key[4];
+    void *hc_alias[4];   // device alias of the page-locked buffer, or NULL
+    bool hc_pinned[4];
     int64_t arena_bytes;
 };
 

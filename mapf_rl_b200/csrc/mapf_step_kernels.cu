@@ -49,8 +49,6 @@ enum : int {
     // diagnosis only (results are WRONG with these set; profiles/step_variants.py uses them to bound the kernel)
     MAPF_STEPF_DIAG_NO_NAVI = 4,   // skip the heuristic-map loads
     MAPF_STEPF_DIAG_NO_STORE = 8,  // skip the observation stores
-    MAPF_STEPF_NO_SPECULATION = 16,  // no speculative L2 prefetch of the heuristic-map line before the step phase
-    MAPF_STEPF_NO_LOOKAHEAD = 32,    // split form: no L2 prefetch of the next environment's inputs
 };
 
 // 4 bits -> 4 bool bytes: bit b lands at bit 8b.  The four shifted copies of x (shifts 0,7,14,21)
@@ -58,33 +56,6 @@ enum : int {
 __device__ __forceinline__ uint32_t expand4(uint32_t x) { return (x * 0x00204081u) & 0x01010101u; }
 
 __device__ __forceinline__ uint32_t smem_addr(const void *ptr) { return (uint32_t)__cvta_generic_to_shared(ptr); }
-__device__ __forceinline__ void prefetch_l2(const void *ptr) { asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr)); }
-
-// the warp asks L2 for every 128-byte line of [ptr, ptr + bytes)
-__device__ __forceinline__ void prefetch_span_l2(const void *ptr, size_t bytes, int lane)
-{
-    const uintptr_t lo = reinterpret_cast<uintptr_t>(ptr) & ~(uintptr_t)127;
-    const uintptr_t hi = reinterpret_cast<uintptr_t>(ptr) + bytes;
-    for (uintptr_t q = lo + (uintptr_t)lane * 128; q < hi; q += 32 * 128) prefetch_l2(reinterpret_cast<const void *>(q));
-}
-
-// Inputs of environment e (positions, goals, actions, step counter, obstacle bitmap) -> L2, one env ahead of use.
-__device__ __forceinline__ void prefetch_env_inputs(const StepParams &p, int e, int lane)
-{
-    const size_t N = p.d.N;
-    if (lane < 8) prefetch_span_l2(p.pos + (size_t)e * N * 2, N * 2, lane);
-    else if (lane < 16) prefetch_span_l2(p.goal + (size_t)e * N * 2, N * 2, lane - 8);
-    else if (lane < 20) prefetch_span_l2(p.actions + (size_t)e * N, N, lane - 16);
-    else if (lane == 20) prefetch_l2(p.steps + e);
-    else if (lane >= 24) {
-        // 8 lanes cover the bitmap (576 B at L = 40, 2816 B at L = 120)
-        const uintptr_t base = reinterpret_cast<uintptr_t>(p.obst + (size_t)e * p.d.obst_stride);
-        const uintptr_t hi = base + (size_t)p.d.obst_stride * 4;
-        for (uintptr_t q = (base & ~(uintptr_t)127) + (uintptr_t)(lane - 24) * 128; q < hi; q += 8 * 128)
-            prefetch_l2(reinterpret_cast<const void *>(q));
-    }
-}
-
 __device__ __forceinline__ void trace_stamp(const StepParams &p, int e, int k, int lane)
 {
     if (p.trace && lane == 0) {
@@ -156,7 +127,7 @@ struct EnvRegs {
 // On return the env's N*486-bit stream sits in s_bits starting at bit `head` (every lane has passed a
 // __syncwarp after its last write), positions / rewards / done / steps are stored, and the agent bitmap
 // still holds this env's bits (clear_agent_bits undoes them).
-template <int RW, int K, bool DO_STEP>
+template <int RW, int K, bool DO_STEP, bool TRACE = false>
 __device__ __forceinline__ void env_step_gather(const StepParams &p, const int e, const int lane, uint32_t *s_obst,
                                                 uint32_t *s_agent, uint32_t *s_bits, uint16_t *s_tgt, uint16_t *s_cell,
                                                 const int head, const uint64_t pol_keep, EnvRegs<K> &out)
@@ -203,24 +174,6 @@ __device__ __forceinline__ void env_step_gather(const StepParams &p, const int e
         if constexpr (DO_STEP)
             if (lane == 0) step_now = p.steps[e];
         if constexpr (DO_STEP) {
-            // Speculation: the heuristic-map line the observation will need is the tile of the cell the agent moves
-            // to if nothing stops it, or of the cell it is on; ask L2 for it now so that the fetch overlaps the
-            // conflict resolution (the real load follows the committed position and then hits L2).
-            if (!(p.flags & MAPF_STEPF_NO_SPECULATION)) {
-#pragma unroll
-                for (int k = 0; k < K; ++k) {
-                    if (valid[k]) {
-                        const int tx = min(max(px[k] + (act[k] == 2) - (act[k] == 1), 0), L - 1);
-                        const int ty = min(max(py[k] + (act[k] == 4) - (act[k] == 3), 0), L - 1);
-                        const char *base = reinterpret_cast<const char *>(p.navi + ((size_t)e * N + k * 32 + lane) * d.navi_agent_stride);
-                        const int t0 = (px[k] >> 3) * d.NB + (py[k] >> 3), t1 = (tx >> 3) * d.NB + (ty >> 3);
-                        prefetch_l2(base + ((size_t)t1 << 7));
-                        if (t1 != t0) prefetch_l2(base + ((size_t)t0 << 7));
-                    }
-                }
-            }
-        }
-        if constexpr (DO_STEP) {
             int tx[K], ty[K], tcell[K], mycell[K], occ_j[K];
             float rew[K];
             bool mover[K], occ_ok[K], fail[K];
@@ -237,7 +190,7 @@ __device__ __forceinline__ void env_step_gather(const StepParams &p, const int e
             }
             asm volatile("cp.async.wait_all;" ::: "memory");
             __syncwarp();  // staged obstacle bitmap, s_cell and s_occ visible to every lane
-            trace_stamp(p, e, 7, lane);
+            if constexpr (TRACE) trace_stamp(p, e, 7, lane);
 #pragma unroll
             for (int k = 0; k < K; ++k) {
                 // stay / move pass, environment.py:298-311
@@ -326,7 +279,7 @@ __device__ __forceinline__ void env_step_gather(const StepParams &p, const int e
                 }
                 if (!__any_sync(MAPF_FULL_MASK, changed)) break;
             }
-            trace_stamp(p, e, 8, lane);
+            if constexpr (TRACE) trace_stamp(p, e, 8, lane);
             // commit, environment.py:410-421
             bool all_goal = true;
 #pragma unroll
@@ -367,7 +320,7 @@ __device__ __forceinline__ void env_step_gather(const StepParams &p, const int e
             __syncwarp();  // s_obst visible
         }
 
-        trace_stamp(p, e, 2, lane);
+        if constexpr (TRACE) trace_stamp(p, e, 2, lane);
         // ---------------- observe, environment.py:433-467 ----------------
         // agent bitmap (environment.py:449-451): one shared-memory atomic per agent
 #pragma unroll
@@ -424,9 +377,9 @@ __device__ __forceinline__ void env_step_gather(const StepParams &p, const int e
                     else S[m] = __funnelshift_l(prev, w, o);
                     prev = w;
                 };
-                if (k == 0) trace_stamp(p, e, 9, lane);
+                if constexpr (TRACE) if (k == 0) trace_stamp(p, e, 9, lane);
                 FieldWalk<0>::run(0ull, val, emit);
-                if (k == 0) trace_stamp(p, e, 10, lane);
+                if constexpr (TRACE) if (k == 0) trace_stamp(p, e, 10, lane);
                 if (((o + 485) >> 5) == 16) S[16] = __funnelshift_l(prev, 0u, o);
             }
             __syncwarp();
@@ -592,11 +545,10 @@ step_split_kernel(const StepParams p)
         for (int e = blockIdx.x * P + warp; e < d.B; e += estride, ++it) {
             const int s = it & 1;
             trace_stamp(p, e, 0, lane);
-            if (e + estride < d.B && !(p.flags & MAPF_STEPF_NO_LOOKAHEAD)) prefetch_env_inputs(p, e + estride, lane);
             mbar_wait(bars + 2 * (2 * warp + s) + 1, ((it >> 1) & 1) ^ 1);  // slot free (first use: passes)
             trace_stamp(p, e, 1, lane);
             EnvRegs<K> r;
-            env_step_gather<RW, K, true>(p, e, lane, s_obst, s_agent, slots + s * slot_words, s_tgt, s_cell, 0, pol_keep, r);
+            env_step_gather<RW, K, true, true>(p, e, lane, s_obst, s_agent, slots + s * slot_words, s_tgt, s_cell, 0, pol_keep, r);
             if (lane == 0) mbar_arrive(bars + 2 * (2 * warp + s));  // every lane's writes precede the last __syncwarp
             trace_stamp(p, e, 3, lane);
             clear_agent_bits<RW, K>(s_agent, r);

@@ -172,7 +172,8 @@ __global__ void l2_retention(uint8_t *dst, const uint8_t *src, size_t nblocks, i
     const size_t w = (size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (w >= nblocks) return;
     size_t h = ((w * 32 + lane) ^ salt) * 0x9E3779B97F4A7C15ull;
-    const size_t line = (h >> 20) % src_lines;
+    // salt == ~0: lane a of warp w reads line 32 w + a (one contiguous 4 KB run per warp: a per-env tile cache)
+    const size_t line = salt == ~0ull ? w * 32 + lane : (h >> 20) % src_lines;
     const uint2 *q = reinterpret_cast<const uint2 *>(src + line * 128);
     uint32_t acc = 0;
 #pragma unroll
@@ -381,6 +382,8 @@ int main(int argc, char **argv)
             }
         }
         CK(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, 0));
+        report("l2ret_SEQUENTIAL_4KB_per_warp_st.cs_ld.plain", (double)nblocks * (blk + 32.0 * 128),
+               time_ms([&](int i) { l2_retention<ST_CS, false><<<grid, warps * 32>>>(slotp(i), src + (size_t)(i % 8) * (64u << 20), nblocks, blk, src_lines, ~0ull, sink); }, iters));
     }
     return 0;
 }
