@@ -50,8 +50,10 @@ __global__ void pack_load_kernel(EnvDims d, const int32_t *__restrict__ env_ids,
 // ---------------------------------------------------------------------------------------------
 // K3: bit-parallel wavefront BFS                                   (environment.py:217-276)
 //
-// Lane l owns map rows l, l+32, ... (RPL rows), each row RW words of padded column bits.  One wave:
-//   new = (frontier shifted to the four neighbours) & free & ~visited
+// Lane l owns the RPL consecutive map rows RPL*l .. RPL*l + RPL - 1 (blocked, so that only the first and
+// the last of them need a neighbour lane: two shuffles per word and wave whatever RPL is), each row RW words
+// of padded column bits.  One wave:
+//   new = (frontier shifted to the four neighbours) & free-and-unvisited
 // and the heuristic bit "neighbour in direction d is strictly closer" (environment.py:260-274) is
 // exactly "this cell is new in wave t and that neighbour was in the frontier of wave t-1", so the
 // four direction planes fall out of the same step and no distance array is needed.
@@ -70,37 +72,31 @@ bfs_navi_kernel(EnvDims d, const int32_t *__restrict__ env_ids, const uint8_t *_
     if (env_mask && !env_mask[e]) return;  // masked re-computation after a device-side reset
     const uint32_t *ob = obst + (size_t)e * d.obst_stride;
 
-    uint32_t fre[RPL][RW], vis[RPL][RW], fro[RPL][RW], pl[4][RPL][RW];
+    // unv = free and not yet visited, fro = frontier of the previous wave, pl = the four heuristic planes
+    uint32_t unv[RPL][RW], fro[RPL][RW], pl[4][RPL][RW];
+    const int gx = goal[((size_t)e * d.N + a) * 2], gy = goal[((size_t)e * d.N + a) * 2 + 1];
 #pragma unroll
     for (int q = 0; q < RPL; ++q) {
-        int row = lane + 32 * q;
+        const int row = lane * RPL + q;
 #pragma unroll
         for (int w = 0; w < RW; ++w) {
             // in-map column mask for this word: padded bits [4, L+4)
             int lo = max(4 - 32 * w, 0), hi = min(d.L + 4 - 32 * w, 32);
             uint32_t cm = 0;
             if (hi > lo) cm = (hi - lo == 32) ? 0xffffffffu : (((1u << (hi - lo)) - 1u) << lo);
-            fre[q][w] = (row < d.L) ? (~ob[(row + 4) * d.RWS + w] & cm) : 0u;
-            vis[q][w] = 0;
-            fro[q][w] = 0;
+            const uint32_t fre = (row < d.L) ? (~__ldg(ob + (row + 4) * d.RWS + w) & cm) : 0u;
+            const int p = gy + 4;
+            fro[q][w] = (row == gx && (p >> 5) == w) ? ((1u << (p & 31)) & fre) : 0u;
+            unv[q][w] = fre & ~fro[q][w];
 #pragma unroll
             for (int k = 0; k < 4; ++k) pl[k][q][w] = 0;
         }
     }
-    const int gx = goal[((size_t)e * d.N + a) * 2], gy = goal[((size_t)e * d.N + a) * 2 + 1];
-#pragma unroll
-    for (int q = 0; q < RPL; ++q)
-#pragma unroll
-        for (int w = 0; w < RW; ++w) {
-            int p = gy + 4;
-            if (lane + 32 * q == gx && (p >> 5) == w) fro[q][w] = (1u << (p & 31)) & fre[q][w];
-            vis[q][w] = fro[q][w];
-        }
 
     int32_t *dist = dist_out ? dist_out + ((size_t)i * d.N + a) * d.L * d.L : nullptr;
     if (dist) {
         for (int q = 0; q < RPL; ++q) {
-            int row = lane + 32 * q;
+            const int row = lane * RPL + q;
             if (row < d.L)
                 for (int y = 0; y < d.L; ++y) dist[row * d.L + y] = MAPF_DIST_UNREACHABLE;
         }
@@ -116,21 +112,20 @@ bfs_navi_kernel(EnvDims d, const int32_t *__restrict__ env_ids, const uint8_t *_
         uint32_t nw[RPL][RW];
         uint32_t any = 0;
 #pragma unroll
-        for (int q = 0; q < RPL; ++q) {
+        for (int w = 0; w < RW; ++w) {
+            // rows of the neighbouring lanes that touch this lane's block
+            uint32_t above = __shfl_up_sync(MAPF_FULL_MASK, fro[RPL - 1][w], 1);
+            uint32_t below = __shfl_down_sync(MAPF_FULL_MASK, fro[0][w], 1);
+            if (lane == 0) above = 0;
+            if (lane == 31) below = 0;
 #pragma unroll
-            for (int w = 0; w < RW; ++w) {
-                uint32_t f = fro[q][w];
-                uint32_t fl = f << 1, fr = f >> 1;
-                if (w > 0) fl |= fro[q][w - 1] >> 31;
-                if (w < RW - 1) fr |= fro[q][w + 1] << 31;
-                uint32_t up = __shfl_up_sync(MAPF_FULL_MASK, f, 1);
-                uint32_t dn = __shfl_down_sync(MAPF_FULL_MASK, f, 1);
-                uint32_t wrap_up = 0, wrap_dn = 0;
-                if (q > 0) wrap_up = __shfl_sync(MAPF_FULL_MASK, fro[q > 0 ? q - 1 : 0][w], 31);
-                if (q < RPL - 1) wrap_dn = __shfl_sync(MAPF_FULL_MASK, fro[q < RPL - 1 ? q + 1 : q][w], 0);
-                if (lane == 0) up = wrap_up;
-                if (lane == 31) dn = wrap_dn;
-                uint32_t x = (fl | fr | up | dn) & fre[q][w] & ~vis[q][w];
+            for (int q = 0; q < RPL; ++q) {
+                const uint32_t f = fro[q][w];
+                const uint32_t fl = w > 0 ? __funnelshift_l(fro[q][w > 0 ? w - 1 : 0], f, 1) : f << 1;
+                const uint32_t fr = w < RW - 1 ? __funnelshift_r(f, fro[q][w < RW - 1 ? w + 1 : w], 1) : f >> 1;
+                const uint32_t up = q > 0 ? fro[q > 0 ? q - 1 : 0][w] : above;
+                const uint32_t dn = q < RPL - 1 ? fro[q < RPL - 1 ? q + 1 : q][w] : below;
+                const uint32_t x = (fl | fr | up | dn) & unv[q][w];
                 nw[q][w] = x;
                 pl[0][q][w] |= x & up;  // neighbour x-1 (row above) is closer   environment.py:260
                 pl[1][q][w] |= x & dn;  // neighbour x+1                          environment.py:264
@@ -144,25 +139,25 @@ bfs_navi_kernel(EnvDims d, const int32_t *__restrict__ env_ids, const uint8_t *_
         for (int q = 0; q < RPL; ++q)
 #pragma unroll
             for (int w = 0; w < RW; ++w) {
-                vis[q][w] |= nw[q][w];
+                unv[q][w] &= ~nw[q][w];
                 fro[q][w] = nw[q][w];
                 if (dist) {
                     uint32_t x = nw[q][w];
                     while (x) {
                         int b = __ffs(x) - 1;
                         x &= x - 1;
-                        dist[(lane + 32 * q) * d.L + (32 * w + b - 4)] = t;
+                        dist[(lane * RPL + q) * d.L + (32 * w + b - 4)] = t;
                     }
                 }
             }
     }
 
-    // emit the overlapping 16x16 tiles (mapf_common.cuh): this lane owns padded row pr = row + 4, which is
+    // emit the overlapping 16x16 tiles (mapf_common.cuh): a map row is padded row pr = row + 4, which is
     // row pr & 7 of tile row-block pr >> 3 and row (pr & 7) + 8 of the block above
     uint2 *nv = reinterpret_cast<uint2 *>(navi + ((size_t)e * d.N + a) * d.navi_agent_stride);
 #pragma unroll
     for (int q = 0; q < RPL; ++q) {
-        const int row = lane + 32 * q;
+        const int row = lane * RPL + q;
         if (row >= d.L) continue;
         const int pr = row + 4, bx1 = pr >> 3, r1 = pr & 7;
 #pragma unroll
