@@ -1,0 +1,31 @@
+#!/usr/bin/env python
+"""Kernel duration of the host-buffer step per MAPF_STEP_HOST_MODE (GPU box; run under
+`ncu --metrics gpu__time_duration.sum` for the kernel times, plain for the end-to-end times)."""
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch  # noqa: E402
+from mapf_rl_b200 import BatchedEnvironment  # noqa: E402
+
+B, N, L = 8192, 32, 40
+env = BatchedEnvironment(B, N, L)
+env.reset(seed=0, density=0.3)
+ring = torch.empty((4, B, N, 6, 9, 9), dtype=torch.uint8, device="cuda")
+rng = np.random.default_rng(0)
+acts = rng.integers(0, 5, size=(16, B, N)).astype(np.uint8)
+steps = int(sys.argv[1]) if len(sys.argv) > 1 else 200
+for s in range(10):
+    env.step_host(acts[s % 16], device_obs=ring[s % 4])
+torch.cuda.synchronize()
+t0 = time.perf_counter()
+for s in range(steps):
+    env.step_host(acts[s % 16], device_obs=ring[s % 4])
+torch.cuda.synchronize()
+el = time.perf_counter() - t0
+print(f"mode {os.environ.get('MAPF_STEP_HOST_MODE', 'default')}: {el / steps * 1e6:.1f} us per host step, "
+      f"{B * N * steps / el / 1e9:.2f} G agent-steps/s")

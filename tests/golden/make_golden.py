@@ -15,6 +15,8 @@ Files (all under tests/golden/):
                           and search.compute_heuristics distance maps for selected goals
   crafted.npz             hand-built conflict cases run through the reference
   per.npz                 buffer.SumTree update/sample rounds and LocalBuffer.finish TD vectors
+  generator_stats.npz     histograms over instances drawn by the reference's own Environment.__init__ / reset()
+                          (density, start-goal distance, component share, components used), SURVEY 8f-3
 """
 from __future__ import annotations
 
@@ -277,10 +279,45 @@ def make_replay():
     print("replay: ok")
 
 
+def make_generator_stats(samples: int = 3000):
+    """Instances drawn by the reference generator itself (environment.py:100-138 in __init__, :146-192 in reset()),
+    summarised by tests/helpers.generator_stats.  get_navi_map (which the constructor and reset() end in) is
+    replaced by a no-op for this run only: it consumes no randomness and does not touch the instance."""
+    import random
+    sys.path.insert(0, os.path.abspath(os.path.join(HERE, "..")))
+    from helpers import GEN_CONFIGS, generator_stats
+    env_mod = ref_loader.load_environment()
+    real_navi = env_mod.Environment.get_navi_map
+    env_mod.Environment.get_navi_map = lambda self: None
+    env_mod.Environment.observe = lambda self: None
+    out = {"samples": np.int64(samples)}
+    try:
+        for L, N in GEN_CONFIGS:
+            np.random.seed(1000 + L)
+            random.seed(2000 + L)
+            maps, agents, goals = [], [], []
+            env = env_mod.Environment(num_agents=N, map_length=L)   # __init__ draws the first instance
+            for k in range(samples):
+                if k:
+                    env.reset()                                     # same procedure, float32 map
+                maps.append(np.asarray(env.map != 0, dtype=np.uint8))
+                agents.append(np.array(env.agents_pos)), goals.append(np.array(env.goals_pos))
+            st = generator_stats(np.stack(maps), np.stack(agents), np.stack(goals))
+            for name, h in st.items():
+                out[f"{name}_{L}_{N}"] = h
+            print("generator stats", L, N, {k: v.tolist() for k, v in st.items()})
+    finally:
+        env_mod.Environment.get_navi_map = real_navi
+    np.savez_compressed(os.path.join(HERE, "generator_stats.npz"), **out)
+
+
 if __name__ == "__main__":
     assert ref_loader.available(), "reference not mounted"
     if len(sys.argv) > 1 and sys.argv[1] == "replay":
         make_replay()
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "generator":
+        make_generator_stats()
         sys.exit(0)
     make_instances()
     make_crafted()
@@ -288,6 +325,7 @@ if __name__ == "__main__":
     make_traces()
     make_navi()
     make_replay()
+    make_generator_stats()
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(HERE, f)))
