@@ -99,7 +99,7 @@ class ClockSampler:
         def run():
             while not self._stop.is_set():
                 self._sample()
-                time.sleep(0.01)
+                time.sleep(0.002)
         self._t = threading.Thread(target=run, daemon=True)
         self._t.start()
 

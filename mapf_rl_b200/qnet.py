@@ -7,6 +7,10 @@ make a batched actor host-bound.  Sub-module names, shapes and construction orde
 reference, so a reference checkpoint (`torch.save(model.state_dict())`, worker.py:338) loads unchanged and a
 same-seed initialisation draws the same weights.  The communication mask comes from the CUDA kernel
 (`BatchedEnvironment.comm_mask`) instead of the per-env topk of model.py:196-208.
+
+For throughput run it as `Network().cuda().eval().to(memory_format=torch.channels_last)` under
+`torch.autocast("cuda", torch.bfloat16)`: 2048 envs x 32 agents take 38 ms in fp32, 24.6 ms with bf16 autocast and
+15.7 ms with NHWC weights on a B200 (profiles/qnet_forward_probe.py) -- still ~700x the env step it follows.
 """
 from __future__ import annotations
 

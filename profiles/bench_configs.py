@@ -186,7 +186,7 @@ def glue_config(torch, out):
     # configs[4]: the actor loop, env batch + Q-net (bf16 autocast) + replay recording
     B, N, L = 2048, 32, 40
     env = BatchedEnvironment(B, N, L, device=dev)
-    net = Network().to(dev).eval()
+    net = Network().to(dev).eval().to(memory_format=torch.channels_last)   # NHWC convs: 24.6 -> 15.7 ms (qnet_forward_probe.py)
     store = ReplayStore(2 * B, max_num_agents=N, device=dev)
     actor = BatchedActor(env, net, store, epsilon=0.1, seed=0, density=0.3)
     with torch.autocast("cuda", dtype=torch.bfloat16):
