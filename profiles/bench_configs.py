@@ -231,6 +231,10 @@ def main():
         env_config(torch, out, "C3 40x40/0.3, 64 agents, 8192 envs", 8192, 64, 40)
     if not want or "C4" in want:
         env_config(torch, out, "C4 80x80/0.3, 64 agents, 4096 envs", 4096, 64, 80, steps=100)
+    if want and "C4B" in want:
+        # same geometry at batch sizes that fill whole waves of the 20 resident warps per SM (2960 per wave)
+        env_config(torch, out, "C4 80x80/0.3, 64 agents, 5920 envs (2 full waves)", 5920, 64, 80, steps=100)
+        env_config(torch, out, "C4 80x80/0.3, 64 agents, 8192 envs", 8192, 64, 80, steps=100)
     if not want or "K4" in want:
         per_config(torch, out)
     if not want or "GLUE" in want:
