@@ -283,9 +283,10 @@ def run_ours(args):
             "clocks": clocks,
             "gpu_launches": args.steps,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * N, "d2h_bytes_per_step": B * N * 4 + B * 5,
-                    "api": "mapf_env_step_host: pinned host actions -> fused kernel, which reads the actions from and stores rewards/done/steps "
-                           "straight into the pinned host buffers over PCIe (zero-copy) -> sync; observations stay in the device "
-                           "replay ring (north star)", "steps": e2e_steps, "host_mode": os.environ.get("MAPF_STEP_HOST_MODE", "2")},
+                    "api": "mapf_env_step_host: pinned host actions (read in place over PCIe) -> step kernel -> observe kernel || "
+                           "D2H rewards/done/steps on a side stream -> sync (one CUDA-graph launch); observations stay in "
+                           "the device replay ring (north star)", "steps": e2e_steps,
+                    "host_mode": os.environ.get("MAPF_STEP_HOST_MODE", "4")},
             "e2e_host_obs": {"value": e2e_obs_value, "unit": UNIT, "h2d_bytes_per_step": B * N,
                              "d2h_bytes_per_step": B * N * 4 + B * 5 + B * N * 486,
                              "api": "same call with the full observation tensor also copied to host (drop-in Environment.step)"},

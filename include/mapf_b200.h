@@ -114,10 +114,12 @@ int mapf_env_observe_rows(mapf_env *env, uint8_t *d_obs_base, const int64_t *d_o
  * kernel, copies rewards / done / steps (and obs if h_obs != NULL) D2H, then synchronises.
  * All h_* buffers are ordinary or page-locked host memory; page-locked ones (cudaHostAlloc /
  * cudaHostRegister / torch pin_memory) are used as DMA endpoints directly, pageable ones are staged through
- * the handle's own pinned area.  By default (MAPF_STEP_HOST_MODE=2) the kernel reads the actions from and
- * stores rewards / done / steps straight into the page-locked buffers through their device alias (PCIe
- * transactions that overlap the kernel) instead of queueing copies around it; MAPF_STEP_HOST_MODE=0 in the
- * environment selects the DMA path, =1 zero-copies only the outputs.  d_obs_opt: if non-NULL the observation is written there (device replay
+ * the handle's own pinned area.  By default the call runs the step kernel (which reads page-locked actions in
+ * place over PCIe), then the observe kernel WHILE rewards / done / steps are copied to the host on a side stream,
+ * the whole sequence captured once per buffer set into a CUDA graph and replayed with one launch; MAPF_STEP_HOST_MODE
+ * in the environment selects the simpler forms (0 = copies around the fused kernel ... 4 = default, see mapf_abi.cu).
+ * What a host pointer resolves to is cached per handle: keep a buffer registered for as long as it is passed.
+ * d_obs_opt: if non-NULL the observation is written there (device replay
  * tensor) instead of an internal buffer. */
 int mapf_env_step_host(mapf_env *env, const uint8_t *h_actions, uint8_t *h_obs, float *h_rewards,
                        uint8_t *h_done, int32_t *h_steps, uint8_t *d_obs_opt, void *stream);

@@ -13,6 +13,7 @@ int mapf_launch_pack_load(mapf_env *, const int32_t *, int, const uint8_t *, con
 int mapf_launch_bfs(mapf_env *, const int32_t *, int, int32_t *, cudaStream_t);
 int mapf_launch_step(mapf_env *, const uint8_t *, uint8_t *, const int64_t *, float *, uint8_t *, int32_t *, cudaStream_t);
 int mapf_launch_observe(mapf_env *, uint8_t *, const int64_t *, uint8_t *, cudaStream_t);
+int mapf_launch_step_only(mapf_env *, const uint8_t *, float *, uint8_t *, int32_t *, cudaStream_t);
 void mapf_set_step_tuning(int, int, int);
 void mapf_set_step_trace(unsigned long long *);
 int mapf_launch_unpack(mapf_env *, uint8_t *, uint8_t *, cudaStream_t);
@@ -74,14 +75,17 @@ T *host_device_alias(T *p)
     return static_cast<T *>(dptr);
 }
 
-// MAPF_STEP_HOST_MODE: 0 = DMA copies either side of the kernel, 1 = the kernel writes rewards / done / steps
-// straight into the caller's page-locked buffers over PCIe (posted writes overlap the kernel),
-// 2 = additionally reads the actions from the caller's page-locked buffer (default).
+// MAPF_STEP_HOST_MODE (measured on 8192 x 32 agents, profiles/e2e_modes.py):
+//   0  DMA copies either side of the fused kernel                                              109 us per call
+//   1  the fused kernel stores rewards / done / steps straight into the page-locked buffers    ~97 us
+//   2  ... and reads the actions in place (the 1 MB of PCIe writes stretches the kernel 33 -> 58 us)   87 us
+//   3  split: step kernel, then the observe kernel while the results are copied on a side stream     88 us
+//   4  the sequence of 3 captured once per buffer set and replayed with one cudaGraphLaunch (default) 78 us
 int step_host_mode()
 {
     static const int m = [] {
         const char *s = std::getenv("MAPF_STEP_HOST_MODE");
-        return s ? std::atoi(s) : 2;
+        return s ? std::atoi(s) : 4;
     }();
     return m;
 }
@@ -205,6 +209,12 @@ int mapf_env_destroy(mapf_env *env)
     cudaFree(env->d_done);
     cudaFree(env->d_steps_out);
     if (env->h_pinned) cudaFreeHost(env->h_pinned);
+    for (auto &c : env->hg)
+        if (c.exec) cudaGraphExecDestroy(c.exec);
+    if (env->cap_stream) cudaStreamDestroy(env->cap_stream);
+    if (env->side_stream) cudaStreamDestroy(env->side_stream);
+    if (env->ev_stepped) cudaEventDestroy(env->ev_stepped);
+    if (env->ev_copied) cudaEventDestroy(env->ev_copied);
     delete env;
     return MAPF_OK;
 }
@@ -345,8 +355,80 @@ int mapf_env_step_host(mapf_env *env, const uint8_t *h_actions, uint8_t *h_obs, 
     float *dst_rew = out_direct ? h_rewards : pin_rew;
     uint8_t *dst_done = out_direct ? h_done : pin_done;
     int32_t *dst_steps = out_direct ? h_steps : pin_steps;
-    // zero-copy: the kernel's own loads / stores reach the host buffers (no DMA launches around the kernel)
     const int mode = step_host_mode();
+    if (mode >= 3) {
+        // split: step kernel -> {observe kernel on `st`  ||  result copies on the side stream} -> join
+        if (!env->side_stream) {
+            MAPF_CUDA(cudaStreamCreateWithFlags(&env->side_stream, cudaStreamNonBlocking));
+            MAPF_CUDA(cudaEventCreateWithFlags(&env->ev_stepped, cudaEventDisableTiming));
+            MAPF_CUDA(cudaEventCreateWithFlags(&env->ev_copied, cudaEventDisableTiming));
+        }
+        const uint8_t *act_dev = act_direct ? static_cast<const uint8_t *>(env->hc_alias[0]) : nullptr;  // read in place over PCIe
+        // issues the whole sequence on `q` (forking to the side stream and joining back)
+        auto enqueue = [&](cudaStream_t q) -> int {
+            const uint8_t *a = act_dev;
+            if (!a) {
+                MAPF_CUDA(cudaMemcpyAsync(env->d_actions, src_act, BN, cudaMemcpyHostToDevice, q));
+                a = env->d_actions;
+            }
+            int r = mapf_launch_step_only(env, a, env->d_rewards, env->d_done, env->d_steps_out, q);
+            if (r != MAPF_OK) return r;
+            MAPF_CUDA(cudaEventRecord(env->ev_stepped, q));
+            MAPF_CUDA(cudaStreamWaitEvent(env->side_stream, env->ev_stepped, 0));
+            MAPF_CUDA(cudaMemcpyAsync(dst_rew, env->d_rewards, BN * 4, cudaMemcpyDeviceToHost, env->side_stream));
+            if (dst_steps)
+                MAPF_CUDA(cudaMemcpyAsync(dst_steps, env->d_steps_out, (size_t)d.B * 4, cudaMemcpyDeviceToHost, env->side_stream));
+            MAPF_CUDA(cudaMemcpyAsync(dst_done, env->d_done, (size_t)d.B, cudaMemcpyDeviceToHost, env->side_stream));
+            MAPF_CUDA(cudaEventRecord(env->ev_copied, env->side_stream));
+            r = mapf_launch_observe(env, obs_dev, nullptr, nullptr, q);
+            if (r != MAPF_OK) return r;
+            if (h_obs) MAPF_CUDA(cudaMemcpyAsync(h_obs, obs_dev, BN * MAPF_OBS_BYTES_PER_AGENT, cudaMemcpyDeviceToHost, q));
+            MAPF_CUDA(cudaStreamWaitEvent(q, env->ev_copied, 0));
+            return MAPF_OK;
+        };
+        if (mode >= 4) {
+            // one cudaGraphLaunch instead of nine stream calls: the sequence is captured per buffer set
+            mapf_env::HostGraph *g = nullptr;
+            for (auto &c : env->hg)
+                if (c.exec && c.act == src_act && c.rew == dst_rew && c.done == dst_done && c.steps == dst_steps && c.hobs == h_obs &&
+                    c.obs_dev == obs_dev)
+                    g = &c;
+            if (!g) {
+                if (!env->cap_stream) MAPF_CUDA(cudaStreamCreateWithFlags(&env->cap_stream, cudaStreamNonBlocking));
+                g = &env->hg[env->hg_next];
+                env->hg_next = (env->hg_next + 1) % 8;
+                if (g->exec) {
+                    cudaGraphExecDestroy(g->exec);
+                    g->exec = nullptr;
+                }
+                cudaGraph_t graph = nullptr;
+                MAPF_CUDA(cudaStreamBeginCapture(env->cap_stream, cudaStreamCaptureModeThreadLocal));
+                rc = enqueue(env->cap_stream);
+                cudaError_t ce = cudaStreamEndCapture(env->cap_stream, &graph);
+                if (rc != MAPF_OK) {
+                    if (graph) cudaGraphDestroy(graph);
+                    return rc;
+                }
+                if (ce != cudaSuccess) return mapf_cuda_fail(ce, "cudaStreamEndCapture");
+                ce = cudaGraphInstantiate(&g->exec, graph, 0);
+                cudaGraphDestroy(graph);
+                if (ce != cudaSuccess) return mapf_cuda_fail(ce, "cudaGraphInstantiate");
+                g->act = src_act, g->rew = dst_rew, g->done = dst_done, g->steps = dst_steps, g->hobs = h_obs, g->obs_dev = obs_dev;
+            }
+            MAPF_CUDA(cudaGraphLaunch(g->exec, st));
+        } else {
+            rc = enqueue(st);
+            if (rc != MAPF_OK) return rc;
+        }
+        MAPF_CUDA(cudaStreamSynchronize(st));
+        if (!out_direct) {
+            std::memcpy(h_rewards, pin_rew, BN * 4);
+            std::memcpy(h_done, pin_done, (size_t)d.B);
+            if (h_steps) std::memcpy(h_steps, pin_steps, (size_t)d.B * 4);
+        }
+        return MAPF_OK;
+    }
+    // zero-copy: the kernel's own loads / stores reach the host buffers (no DMA launches around the kernel)
     float *zc_rew = nullptr;
     uint8_t *zc_done = nullptr;
     int32_t *zc_steps = nullptr;

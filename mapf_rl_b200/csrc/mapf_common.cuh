@@ -61,6 +61,15 @@ struct mapf_env {
     // last caller buffers of mapf_env_step_host and what they resolved to (a per-step actor reuses its buffers, so
     // the four cudaPointerGetAttributes / cudaHostGetDevicePointer queries are paid once)
     uint8_t *pin_alias;  // device alias of h_pinned
+    cudaStream_t side_stream;          // result copies of mapf_env_step_host run here, next to the observe kernel
+    cudaEvent_t ev_stepped, ev_copied;
+    // the same sequence captured once per (buffer set, observation target) and replayed with one launch
+    struct HostGraph {
+        const void *act, *rew, *done, *steps, *hobs, *obs_dev;
+        cudaGraphExec_t exec;
+    } hg[8];
+    int hg_next;
+    cudaStream_t cap_stream;
     const void *hc_key[4];
     void *hc_alias[4];   // device alias of the page-locked buffer, or NULL
     bool hc_pinned[4];

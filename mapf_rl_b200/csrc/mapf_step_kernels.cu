@@ -127,7 +127,7 @@ struct EnvRegs {
 // On return the env's N*486-bit stream sits in s_bits starting at bit `head` (every lane has passed a
 // __syncwarp after its last write), positions / rewards / done / steps are stored, and the agent bitmap
 // still holds this env's bits (clear_agent_bits undoes them).
-template <int RW, int K, bool DO_STEP, bool TRACE = false>
+template <int RW, int K, bool DO_STEP, bool TRACE = false, bool DO_OBS = true>
 __device__ __forceinline__ void env_step_gather(const StepParams &p, const int e, const int lane, uint32_t *s_obst,
                                                 uint32_t *s_agent, uint32_t *s_bits, uint16_t *s_tgt, uint16_t *s_cell,
                                                 const int head, const uint64_t pol_keep, EnvRegs<K> &out)
@@ -321,6 +321,7 @@ __device__ __forceinline__ void env_step_gather(const StepParams &p, const int e
         }
 
         if constexpr (TRACE) trace_stamp(p, e, 2, lane);
+        if constexpr (DO_OBS) {
         // ---------------- observe, environment.py:433-467 ----------------
         // agent bitmap (environment.py:449-451): one shared-memory atomic per agent
 #pragma unroll
@@ -390,6 +391,7 @@ __device__ __forceinline__ void env_step_gather(const StepParams &p, const int e
             }
             __syncwarp();
         }
+        }  // DO_OBS
 
 #pragma unroll
         for (int k = 0; k < K; ++k) {
@@ -476,6 +478,27 @@ step_observe_kernel(const StepParams p)
         __syncwarp();
         clear_agent_bits<RW, K>(s_agent, r);  // the agent bits this env set
     }
+}
+
+// ---- K1 alone: Environment.step without the observation.  mapf_env_step_host launches it ahead of the observe kernel
+// so that the device-to-host copies of rewards / done / steps run WHILE the observation is being written (their
+// 1 MB of PCIe traffic otherwise follows, or stretches, the fused kernel).
+template <int RW, int K>
+__global__ void __launch_bounds__(128)
+step_only_kernel(const StepParams p)
+{
+    extern __shared__ __align__(16) uint32_t smem[];
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    uint32_t *s_obst = smem + (size_t)warp * p.warp_smem_words;
+    uint32_t *s_agent = s_obst + p.obst_words;
+    uint32_t *s_bits = s_agent + p.obst_words;
+    uint16_t *s_tgt = reinterpret_cast<uint16_t *>(s_bits + p.bits_words);
+    uint16_t *s_cell = s_tgt + 32 * K;
+    const int e = blockIdx.x * 4 + warp;
+    if (e >= p.d.B) return;
+    EnvRegs<K> r;
+    env_step_gather<RW, K, true, false, false>(p, e, lane, s_obst, s_agent, s_bits, s_tgt, s_cell, 0, 0ull, r);
 }
 
 // ---- K1+K2, split form (the hot path) -----------------------------------------------------------------
@@ -804,6 +827,51 @@ int mapf_launch_step(mapf_env *env, const uint8_t *d_actions, uint8_t *d_obs, co
         if (rc != MAPF_EINVAL) return rc;
     }
     return launch_step<true>(env, p, st);
+}
+
+template <int RW, int K>
+static int launch_step_only_cfg(mapf_env *env, const StepParams &p, cudaStream_t st)
+{
+    auto kern = step_only_kernel<RW, K>;
+    const size_t smem = (size_t)p.warp_smem_words * 4 * 4;
+    if (smem > 227 * 1024) {
+        mapf_set_error("map too large for the step kernel's shared memory");
+        return MAPF_EINVAL;
+    }
+    if (smem > 48 * 1024) MAPF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<(env->d.B + 3) / 4, 128, smem, st>>>(p);
+    MAPF_CUDA(cudaGetLastError());
+    return MAPF_OK;
+}
+
+int mapf_launch_step_only(mapf_env *env, const uint8_t *d_actions, float *d_rewards, uint8_t *d_done, int32_t *d_steps,
+                          cudaStream_t st)
+{
+    StepParams p = make_params(env);
+    p.actions = d_actions;
+    p.rewards = d_rewards;
+    p.done = d_done;
+    p.steps_out = d_steps;
+    switch (env->d.RW * 10 + env->d.K) {
+        case 11: return launch_step_only_cfg<1, 1>(env, p, st);
+        case 12: return launch_step_only_cfg<1, 2>(env, p, st);
+        case 13: return launch_step_only_cfg<1, 3>(env, p, st);
+        case 14: return launch_step_only_cfg<1, 4>(env, p, st);
+        case 21: return launch_step_only_cfg<2, 1>(env, p, st);
+        case 22: return launch_step_only_cfg<2, 2>(env, p, st);
+        case 23: return launch_step_only_cfg<2, 3>(env, p, st);
+        case 24: return launch_step_only_cfg<2, 4>(env, p, st);
+        case 31: return launch_step_only_cfg<3, 1>(env, p, st);
+        case 32: return launch_step_only_cfg<3, 2>(env, p, st);
+        case 33: return launch_step_only_cfg<3, 3>(env, p, st);
+        case 34: return launch_step_only_cfg<3, 4>(env, p, st);
+        case 41: return launch_step_only_cfg<4, 1>(env, p, st);
+        case 42: return launch_step_only_cfg<4, 2>(env, p, st);
+        case 43: return launch_step_only_cfg<4, 3>(env, p, st);
+        case 44: return launch_step_only_cfg<4, 4>(env, p, st);
+    }
+    mapf_set_error("unsupported geometry");
+    return MAPF_EINVAL;
 }
 
 int mapf_launch_observe(mapf_env *env, uint8_t *d_obs, const int64_t *d_obs_rows, uint8_t *d_pos, cudaStream_t st)

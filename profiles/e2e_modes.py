@@ -29,3 +29,21 @@ torch.cuda.synchronize()
 el = time.perf_counter() - t0
 print(f"mode {os.environ.get('MAPF_STEP_HOST_MODE', 'default')}: {el / steps * 1e6:.1f} us per host step, "
       f"{B * N * steps / el / 1e9:.2f} G agent-steps/s")
+# GPU span of one host step (events on the stream around the call) next to its wall time
+spans, walls = [], []
+for s in range(50):
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    e0.record()
+    env.step_host(acts[s % 16], device_obs=ring[s % 4])
+    e1.record()
+    walls.append(time.perf_counter() - t0)
+    torch.cuda.synchronize()
+    spans.append(e0.elapsed_time(e1) * 1e3)
+print(f"   GPU span median {np.median(spans):.1f} us, wall median {np.median(walls) * 1e6:.1f} us (includes the two event records)")
+# host-side cost of the call path alone: copy of the actions into the pinned buffer
+hb = env.host_actions
+t0 = time.perf_counter()
+for s in range(200):
+    np.copyto(hb, acts[s % 16])
+print(f"   np.copyto of the actions: {(time.perf_counter() - t0) / 200 * 1e6:.1f} us")
