@@ -131,6 +131,8 @@ int mapf_env_step_host(mapf_env *env, const uint8_t *h_actions, uint8_t *h_obs, 
  *   ctas_per_sm cap on resident CTAs per SM (0 = as many as fit); < 0 keeps
  * The same three values are read once from MAPF_STEP_VARIANT / MAPF_STEP_FLAGS / MAPF_STEP_CTAS_PER_SM. */
 int mapf_debug_step_tuning(int32_t variant, int32_t flags, int32_t ctas_per_sm);
+/* Selects the form of mapf_env_step_host (0..4, see there; < 0 only queries); returns the mode in force. */
+int mapf_debug_step_host_mode(int32_t mode);
 /* Diagnosis: while d_trace != NULL (u64[B, 16], device) the split step kernel stamps %globaltimer per environment:
  * [0] producer reaches the env, [1] its slot is free, [7] inputs loaded, [8] conflicts resolved, [2] step phase
  * done (state stored), [9] before / [10] after the window gather of agent 0, [3] bit stream published,

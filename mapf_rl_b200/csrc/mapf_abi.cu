@@ -81,14 +81,15 @@ T *host_device_alias(T *p)
 //   2  ... and reads the actions in place (the 1 MB of PCIe writes stretches the kernel 33 -> 58 us)   87 us
 //   3  split: step kernel, then the observe kernel while the results are copied on a side stream     88 us
 //   4  the sequence of 3 captured once per buffer set and replayed with one cudaGraphLaunch (default) 78 us
-int step_host_mode()
+int &step_host_mode_ref()
 {
-    static const int m = [] {
+    static int m = [] {
         const char *s = std::getenv("MAPF_STEP_HOST_MODE");
         return s ? std::atoi(s) : 4;
     }();
     return m;
 }
+int step_host_mode() { return step_host_mode_ref(); }
 
 template <typename T>
 int dev_alloc(T **p, size_t count, int64_t *total)
@@ -484,6 +485,12 @@ int mapf_debug_step_tuning(int32_t variant, int32_t flags, int32_t ctas_per_sm)
 {
     mapf_set_step_tuning(variant, flags, ctas_per_sm);
     return MAPF_OK;
+}
+
+int mapf_debug_step_host_mode(int32_t mode)
+{
+    if (mode >= 0) step_host_mode_ref() = mode;
+    return step_host_mode_ref();
 }
 
 int mapf_debug_step_trace(uint64_t *d_trace)

@@ -264,6 +264,51 @@ def test_step_host_entry_point():
         assert int(od) == done[k] and steps[k] == 1
 
 
+@pytest.mark.parametrize("mode", [0, 1, 2, 3, 4])
+@pytest.mark.parametrize("pinned", [True, False])
+def test_step_host_every_mode(mode, pinned):
+    """Every form of the host-buffer step (copies around the fused kernel, zero-copy results, zero-copy actions, split
+    step / observe with overlapped copies, the same from a CUDA graph) with page-locked and pageable caller buffers:
+    several consecutive steps (graph replay with changing observation targets), bit-exact against the oracle."""
+    import ctypes as C
+    import torch
+    from mapf_rl_b200 import _native
+    lib = _native.lib()
+    prev = lib.mapf_debug_step_host_mode(-1)
+    try:
+        assert lib.mapf_debug_step_host_mode(mode) == mode
+        maps, agents, goals = instances(32)
+        B, N = 70, 32
+        env = make_env(B, N, 40)
+        env.load(maps[:B], agents[:B], goals[:B])
+        ora = []
+        for k in range(B):
+            o = oracle.OracleEnv()
+            o.load(maps[k], agents[k], goals[k])
+            ora.append(o)
+        mk = (lambda shape, dt: torch.zeros(shape, dtype=dt, pin_memory=True).numpy()) if pinned else \
+             (lambda shape, dt: torch.zeros(shape, dtype=dt).numpy())
+        acts, rew = mk((B, N), torch.uint8), mk((B, N), torch.float32)
+        done, steps = mk((B,), torch.uint8), mk((B,), torch.int32)
+        ring = torch.zeros((3, B, N, 6, 9, 9), dtype=torch.uint8, device="cuda:0")
+        vp = lambda a: a.ctypes.data_as(C.c_void_p)
+        rng = np.random.default_rng(mode)
+        for s in range(7):
+            acts[:] = rng.integers(0, 5, size=(B, N))
+            slot = ring[s % 3]
+            _native.check(lib.mapf_env_step_host(env._h, vp(acts), None, vp(rew), vp(done), vp(steps),
+                                                 C.c_void_p(slot.data_ptr()), env._stream()))
+            obs = slot.cpu().numpy()
+            for k in range(B):
+                (oo, op), orw, od, _ = ora[k].step(acts[k])
+                assert np.array_equal(oo.astype(np.uint8), obs[k]), (mode, s, k)
+                assert np.array_equal(np.asarray(orw, dtype=np.float32), rew[k]), (mode, s, k)
+                assert int(od) == done[k] and steps[k] == s + 1
+        env.check()
+    finally:
+        lib.mapf_debug_step_host_mode(prev)
+
+
 def test_step_host_pageable_caller_buffers():
     """mapf_env_step_host with ordinary (pageable) numpy buffers goes through the handle's pinned staging area."""
     import ctypes as C
