@@ -210,7 +210,7 @@ def run_ours(args):
     g = torch.Generator(device=dev)
     g.manual_seed(args.seed + rank)
     actions = torch.randint(0, 5, (A, B, N), generator=g, device=dev, dtype=torch.uint8)
-    actions_host = actions.cpu().numpy()
+    actions_host = actions.cpu().pin_memory()  # [A,B,N] page-locked: step_host hands slot s % A to the GPU in place
 
     def barrier():
         if world > 1:
@@ -229,19 +229,43 @@ def run_ours(args):
         torch.cuda.synchronize(dev)
     env.check()
 
-    # ---- timed region: exactly K steps, device-resident inputs, one kernel launch per step ------
+    # ---- timed region: exactly K steps, device-resident inputs -----------------------------------
+    # mapf_env_rollout: the K steps of the whole batch as `chains` independent sub-batch chains on internal streams
+    # (environments are independent; step t+1 of a sub-batch waits for step t of that sub-batch only)
+    out_ring = 2
+    chains, per, graph_period = env.rollout_plan(args.steps, A, R, out_ring, args.chains)
+    rew_ring = torch.empty((out_ring, B, N), dtype=torch.float32, device=dev)
+    done_ring = torch.empty((out_ring, B), dtype=torch.uint8, device=dev)
+    steps_ring = torch.empty((out_ring, B), dtype=torch.int32, device=dev)
+
+    def rollout(k):
+        env.rollout(actions, num_steps=k, out_obs=replay, out_rewards=rew_ring, out_done=done_ring, out_steps=steps_ring,
+                    chains=args.chains)
+
+    rollout(64)
+    torch.cuda.synchronize(dev)
     sampler = ClockSampler(local)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     sampler.start()
     ev0.record()
-    for s in range(args.steps):
-        env.step(actions[s % A], out_obs=replay[s % R])
+    rollout(args.steps)
     ev1.record()
     barrier()
     clocks = sampler.stop()
     ms = sharding.max_over_ranks(ev0.elapsed_time(ev1), dev)
     value = world * B * N * args.steps / (ms * 1e-3)
+    env.check()
+
+    # ---- the same K steps as one whole-batch launch per step (mapf_env_step_observe from Python) ----
+    ev2, ev3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev2.record()
+    for s in range(args.steps):
+        env.step(actions[s % A], out_obs=replay[s % R])
+    ev3.record()
+    barrier()
+    ms_single = sharding.max_over_ranks(ev2.elapsed_time(ev3), dev)
 
     # ---- e2e: through the host-buffer C-ABI entry point (mapf_env_step_host) ---------------------
     def e2e_run(steps, want_obs):
@@ -281,9 +305,16 @@ def run_ours(args):
                              f"({R * B * N * 486 / 1e6:.0f} MB) + {env.arena_bytes / 1e6:.0f} MB state arena, both > 126 MB L2",
                        "extra_warmup": "0.3 s of untimed steps after W so SM clocks are under load"},
             "clocks": clocks,
-            "gpu_launches": args.steps,
+            "gpu_launches": args.steps * chains,
+            "launch": {"api": "mapf_env_rollout (one call for the K steps)", "chains": chains, "envs_per_chain": per,
+                       "graph_period_steps": graph_period,
+                       "note": "each step of the batch = `chains` launches of step_observe_kernel over disjoint env ranges on "
+                               "internal streams; chains run out of phase, so one's stores overlap another's conflict resolution"},
+            "single_launch": {"api": "mapf_env_step_observe, one whole-batch launch per step", "ms_per_step": ms_single / args.steps,
+                              "value": world * B * N * args.steps / (ms_single * 1e-3),
+                              "roofline_frac": algo_bytes(N, L) * B * N / (ms_single * 1e-3 / args.steps) / 1e9 / peak},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * N, "d2h_bytes_per_step": B * N * 4 + B * 5,
-                    "api": "mapf_env_step_host: pinned host actions (read in place over PCIe) -> step kernel -> observe kernel || "
+                    "api": "mapf_env_step_host on one of 16 page-locked action buffers (read in place over PCIe) -> step kernel -> observe kernel || "
                            "D2H rewards/done/steps on a side stream -> sync (one CUDA-graph launch); observations stay in "
                            "the device replay ring (north star)", "steps": e2e_steps,
                     "host_mode": os.environ.get("MAPF_STEP_HOST_MODE", "4")},
@@ -292,6 +323,9 @@ def run_ours(args):
                              "api": "same call with the full observation tensor also copied to host (drop-in Environment.step)"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "kernel": "step_observe_kernel<RW=2,K=1,DO_STEP,4 warps,12 CTAs/SM>",
+                         "achieved_is": "algorithmic bytes of one whole-batch step / step period in the timed region (the "
+                                        f"{chains} sub-batch launches of a step overlap those of its neighbours); `traffic` is "
+                                        "the ncu DRAM bytes of a whole-batch launch",
                          "algorithmic_bytes_per_agent_step": algo_bytes(N, L), "peak_source": peak_src,
                          "note": "peak = measured copy (read+write) bandwidth; what plain write / mixed streams of this "
                                  "shape reach on a B200 is in profiles/r1_membw_probe.jsonl"},
@@ -321,6 +355,7 @@ def main():
     ap.add_argument("--density", type=float, default=0.3)
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--obs-ring", type=int, default=4)
+    ap.add_argument("--chains", type=int, default=0, help="sub-batch chains of mapf_env_rollout (0 = library default)")
     ap.add_argument("--ref-envs", type=int, default=4096)
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -110,6 +110,31 @@ int mapf_env_step_observe_rows(mapf_env *env, const uint8_t *d_actions, uint8_t 
                                float *d_rewards, uint8_t *d_done, int32_t *d_steps, void *stream);
 int mapf_env_observe_rows(mapf_env *env, uint8_t *d_obs_base, const int64_t *d_obs_rows, uint8_t *d_pos, void *stream);
 
+/* T lockstep steps with the actions already resident on the device: the loop `for t: obs, r, done, _ = env.step(a[t])`
+ * of test.py:120-130 / worker.py:383-395 when the actions do not depend on the observations (replaying planner paths,
+ * random-policy data generation, benchmarking).  Step t reads action slot t % action_slots, writes observation slot
+ * t % obs_slots and rewards / done / steps slot t % out_slots; results equal T calls of mapf_env_step_observe.
+ *   d_actions u8[action_slots, B, N]   d_obs u8[obs_slots, B, N, 6, 9, 9]
+ *   d_rewards f32[out_slots, B, N]     d_done u8[out_slots, B]     d_steps i32[out_slots, B] (optional)
+ * Environments are independent (no reference code path couples two Environment objects), so the batch runs as `chains`
+ * contiguous sub-batches (1..MAPF_MAX_CHAINS; 0 = default: 1 below 2048 environments, else 4, or 8 when the rollout is long
+ * enough to be replayed from graphs), each an independent chain of T launches on a stream of its own: launch t+1 of a chain
+ * waits for launch t of THAT chain only, the chains drift out of phase, and the observation stores of one overlap the
+ * conflict resolution of another (one launch over the whole batch keeps every warp in the same phase: 34 us per step at
+ * 8192 x 32 agents, 25.7 us as 8 chains; profiles/).  When T covers at least 4 periods P = lcm(slot counts) <= 64, whole
+ * periods are replayed from per-chain CUDA graphs captured once per argument set (the host cost of a launch, ~4 us, would
+ * otherwise bound 8 chains at 32 us per step).
+ * The call forks from `stream` and joins back into it; it returns when everything is queued (asynchronous). */
+#define MAPF_MAX_CHAINS 16
+int mapf_env_rollout(mapf_env *env, int32_t T, const uint8_t *d_actions, int32_t action_slots, uint8_t *d_obs,
+                     int32_t obs_slots, float *d_rewards, uint8_t *d_done, int32_t *d_steps, int32_t out_slots,
+                     int32_t chains, void *stream);
+
+/* How mapf_env_rollout would run these arguments: number of chains, environments per chain, and the number of steps per
+ * replayed graph (0 = every step launched directly).  Outputs are optional. */
+int mapf_env_rollout_plan(mapf_env *env, int32_t T, int32_t action_slots, int32_t obs_slots, int32_t out_slots,
+                          int32_t chains, int32_t *chains_out, int32_t *envs_per_chain_out, int32_t *graph_period_out);
+
 /* Host-buffer variant of step (what a per-process actor calls): copies actions H2D, runs the fused
  * kernel, copies rewards / done / steps (and obs if h_obs != NULL) D2H, then synchronises.
  * All h_* buffers are ordinary or page-locked host memory; page-locked ones (cudaHostAlloc /

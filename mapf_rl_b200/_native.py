@@ -43,6 +43,8 @@ SIGNATURES = {
     "mapf_env_observe": (C.c_int, [_vp, _vp, _vp, _vp]),
     "mapf_env_step_observe_rows": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "mapf_env_observe_rows": (C.c_int, [_vp, _vp, _vp, _vp, _vp]),
+    "mapf_env_rollout": (C.c_int, [_vp, _i32, _vp, _i32, _vp, _i32, _vp, _vp, _vp, _i32, _i32, _vp]),
+    "mapf_env_rollout_plan": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp]),
     "mapf_env_step_host": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "mapf_debug_step_tuning": (C.c_int, [_i32, _i32, _i32]),
     "mapf_debug_step_trace": (C.c_int, [_vp]),

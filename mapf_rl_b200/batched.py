@@ -136,6 +136,43 @@ class BatchedEnvironment:
                                                       C.c_void_p(self._steps.data_ptr()), self._stream()))
         return obs, rewards, done
 
+    def rollout(self, actions, num_steps: Optional[int] = None, out_obs=None, out_rewards=None, out_done=None,
+                out_steps=None, chains: int = 0):
+        """`num_steps` lockstep steps with the actions already on the device (mapf_env_rollout): the loop
+        `for t: env.step(actions[t])` of test.py:120-130 when the actions do not depend on the observations.
+        actions uint8[A,B,N] (step t uses slot t % A; num_steps defaults to A); out_obs uint8[R,B,N,6,9,9],
+        out_rewards float32[S,B,N], out_done uint8[S,B], out_steps int32[S,B] are rings indexed t % R / t % S
+        (allocated with one slot per step when not given).  The batch runs as `chains` independent sub-batch chains
+        on internal streams (0 = default).  Asynchronous on the current stream.
+        Returns (obs, rewards, done, steps) rings."""
+        torch = _torch()
+        B, N = self.num_envs, self.num_agents
+        assert isinstance(actions, torch.Tensor) and actions.is_cuda and actions.dtype == torch.uint8 and actions.is_contiguous()
+        assert actions.dim() == 3 and tuple(actions.shape[1:]) == (B, N), "actions number"
+        A = int(actions.shape[0])
+        T = A if num_steps is None else int(num_steps)
+        obs = out_obs if out_obs is not None else torch.empty((T, B, N, *self.OBS_SHAPE), dtype=torch.uint8, device=self.device)
+        rewards = out_rewards if out_rewards is not None else torch.empty((T, B, N), dtype=torch.float32, device=self.device)
+        S = int(rewards.shape[0])
+        done = out_done if out_done is not None else torch.empty((S, B), dtype=torch.uint8, device=self.device)
+        steps = out_steps if out_steps is not None else torch.empty((S, B), dtype=torch.int32, device=self.device)
+        assert obs.is_contiguous() and obs.dtype == torch.uint8 and tuple(obs.shape[1:]) == (B, N, *self.OBS_SHAPE)
+        assert rewards.is_contiguous() and rewards.dtype == torch.float32 and tuple(rewards.shape) == (S, B, N)
+        assert done.is_contiguous() and done.dtype == torch.uint8 and tuple(done.shape) == (S, B)
+        assert steps.is_contiguous() and steps.dtype == torch.int32 and tuple(steps.shape) == (S, B)
+        _native.check(self._lib.mapf_env_rollout(
+            self._h, T, C.c_void_p(actions.data_ptr()), A, C.c_void_p(obs.data_ptr()), int(obs.shape[0]),
+            C.c_void_p(rewards.data_ptr()), C.c_void_p(done.data_ptr()), C.c_void_p(steps.data_ptr()), S, int(chains),
+            self._stream()))
+        return obs, rewards, done, steps
+
+    def rollout_plan(self, num_steps: int, action_slots: int, obs_slots: int, out_slots: int, chains: int = 0):
+        """-> (chains, envs_per_chain, graph_period) mapf_env_rollout would use (graph_period 0 = direct launches)."""
+        out = [C.c_int32() for _ in range(3)]
+        _native.check(self._lib.mapf_env_rollout_plan(self._h, int(num_steps), int(action_slots), int(obs_slots), int(out_slots),
+                                                     int(chains), *[C.byref(o) for o in out]))
+        return tuple(o.value for o in out)
+
     def observe(self, out_obs=None, obs_rows=None):
         """-> (obs uint8[B,N,6,9,9], pos uint8[B,N,2])   (environment.py:433-467); `obs_rows` as in step()."""
         torch = _torch()
@@ -186,16 +223,26 @@ class BatchedEnvironment:
         return self._host_buffers(False)["actions_np"]
 
     def step_host(self, actions: np.ndarray, want_obs: bool = False, device_obs=None):
-        """Host-buffer step through mapf_env_step_host: numpy in, numpy out, synchronous.
+        """Host-buffer step through mapf_env_step_host: numpy (or a page-locked uint8 torch CPU tensor) in, numpy out,
+        synchronous.
         Returns (obs | None, rewards, done, steps) as numpy VIEWS of page-locked buffers owned by this object:
         they are overwritten by the next step_host call (copy them to keep them)."""
         B, N = self.num_envs, self.num_agents
         hb = self._host_buffers(want_obs)
-        if actions is not hb["actions_np"]:   # the caller may fill env.host_actions in place instead
+        pa, pr, pd, ps = hb["ptrs"]
+        torch = _torch()
+        if isinstance(actions, torch.Tensor):
+            # a page-locked uint8 CPU tensor (torch pin_memory) is read by the GPU in place: no staging copy
+            assert (actions.device.type == "cpu" and actions.dtype == torch.uint8 and actions.is_contiguous()
+                    and tuple(actions.shape) == (B, N)), "actions number"
+            if actions.is_pinned():
+                pa = C.c_void_p(actions.data_ptr())
+            else:
+                np.copyto(hb["actions_np"], actions.numpy())
+        elif actions is not hb["actions_np"]:   # the caller may fill env.host_actions in place instead
             a = np.asarray(actions)
             assert a.shape == (B, N), "actions number"
             np.copyto(hb["actions_np"], a, casting="unsafe")
-        pa, pr, pd, ps = hb["ptrs"]
         _native.check(self._lib.mapf_env_step_host(
             self._h, pa, hb["obs"].data_ptr() if want_obs else None, pr, pd, ps,
             C.c_void_p(device_obs.data_ptr()) if device_obs is not None else None, self._stream()))

@@ -14,7 +14,9 @@ int mapf_launch_bfs(mapf_env *, const int32_t *, int, int32_t *, cudaStream_t);
 int mapf_launch_step(mapf_env *, const uint8_t *, uint8_t *, const int64_t *, float *, uint8_t *, int32_t *, cudaStream_t);
 int mapf_launch_observe(mapf_env *, uint8_t *, const int64_t *, uint8_t *, cudaStream_t);
 int mapf_launch_step_only(mapf_env *, const uint8_t *, float *, uint8_t *, int32_t *, cudaStream_t);
+int mapf_launch_step_range(mapf_env *, int, int, const uint8_t *, uint8_t *, float *, uint8_t *, int32_t *, cudaStream_t);
 void mapf_set_step_tuning(int, int, int);
+int mapf_step_tuning_generation();
 void mapf_set_step_trace(unsigned long long *);
 int mapf_launch_unpack(mapf_env *, uint8_t *, uint8_t *, cudaStream_t);
 int mapf_launch_comm_mask(mapf_env *, int, uint8_t *, cudaStream_t);
@@ -81,6 +83,8 @@ T *host_device_alias(T *p)
 //   2  ... and reads the actions in place (the 1 MB of PCIe writes stretches the kernel 33 -> 58 us)   87 us
 //   3  split: step kernel, then the observe kernel while the results are copied on a side stream     88 us
 //   4  the sequence of 3 captured once per buffer set and replayed with one cudaGraphLaunch (default) 78 us
+// Measured and dropped: the batch as 2 / 4 / 8 sub-batch chains, each {actions -> fused kernel -> results} on its own stream
+// inside the graph (105 / 124 / 160 us: every extra DMA node costs more than the overlap returns; profiles/r1_e2e_chains.log).
 int &step_host_mode_ref()
 {
     static int m = [] {
@@ -90,7 +94,6 @@ int &step_host_mode_ref()
     return m;
 }
 int step_host_mode() { return step_host_mode_ref(); }
-
 template <typename T>
 int dev_alloc(T **p, size_t count, int64_t *total)
 {
@@ -213,6 +216,14 @@ int mapf_env_destroy(mapf_env *env)
     for (auto &c : env->hg)
         if (c.exec) cudaGraphExecDestroy(c.exec);
     if (env->cap_stream) cudaStreamDestroy(env->cap_stream);
+    for (int j = 0; j < MAPF_MAX_CHAINS; ++j) {
+        if (env->chain_stream[j]) cudaStreamDestroy(env->chain_stream[j]);
+        if (env->chain_done[j]) cudaEventDestroy(env->chain_done[j]);
+    }
+    if (env->chain_fork) cudaEventDestroy(env->chain_fork);
+    for (auto &g : env->rg)
+        for (auto &x : g.exec)
+            if (x) cudaGraphExecDestroy(x);
     if (env->side_stream) cudaStreamDestroy(env->side_stream);
     if (env->ev_stepped) cudaEventDestroy(env->ev_stepped);
     if (env->ev_copied) cudaEventDestroy(env->ev_copied);
@@ -303,6 +314,156 @@ int mapf_env_observe(mapf_env *env, uint8_t *d_obs, uint8_t *d_pos, void *stream
     return mapf_launch_observe(env, d_obs, nullptr, d_pos, static_cast<cudaStream_t>(stream));
 }
 
+namespace {
+// How mapf_env_rollout runs T steps: S chains of `per` environments each; P > 0 when whole slot periods of P steps are
+// replayed from per-chain captured graphs.
+struct RolloutPlan {
+    int S, per, P;
+    bool graphs;
+};
+RolloutPlan rollout_plan(const EnvDims &d, int T, int action_slots, int obs_slots, int out_slots, int chains, bool capturing)
+{
+    auto gcd = [](int a, int b) { while (b) { int r = a % b; a = b; b = r; } return a; };
+    auto lcm_cap = [&](int a, int b) { const long long l = (long long)a / gcd(a, b) * b; return l > 64 ? 65 : (int)l; };
+    RolloutPlan pl;
+    pl.P = lcm_cap(lcm_cap(action_slots, obs_slots), out_slots);
+    pl.graphs = pl.P <= 64 && T >= 4 * pl.P && d.B >= 2048 && chains != 1 && !capturing;
+    // sub-batches are multiples of 4 environments (one CTA of the step kernel serves 4)
+    pl.S = chains ? chains : (d.B >= 2048 ? (pl.graphs ? 8 : 4) : 1);
+    pl.per = (((d.B + pl.S - 1) / pl.S) + 3) & ~3;
+    pl.S = (d.B + pl.per - 1) / pl.per;
+    if (pl.S == 1) pl.graphs = false;
+    return pl;
+}
+}  // namespace
+
+int mapf_env_rollout_plan(mapf_env *env, int32_t T, int32_t action_slots, int32_t obs_slots, int32_t out_slots, int32_t chains,
+                          int32_t *chains_out, int32_t *envs_per_chain_out, int32_t *graph_period_out)
+{
+    REQUIRE_ENV(env);
+    if (T < 0 || action_slots < 1 || obs_slots < 1 || out_slots < 1 || chains < 0 || chains > MAPF_MAX_CHAINS) {
+        mapf_set_error("mapf_env_rollout_plan: T >= 0, slot counts >= 1 and 0 <= chains <= 16 required");
+        return MAPF_EINVAL;
+    }
+    const RolloutPlan pl = rollout_plan(env->d, T, action_slots, obs_slots, out_slots, chains, false);
+    if (chains_out) *chains_out = pl.S;
+    if (envs_per_chain_out) *envs_per_chain_out = pl.per;
+    if (graph_period_out) *graph_period_out = pl.graphs ? pl.P : 0;
+    return MAPF_OK;
+}
+
+int mapf_env_rollout(mapf_env *env, int32_t T, const uint8_t *d_actions, int32_t action_slots, uint8_t *d_obs, int32_t obs_slots,
+                     float *d_rewards, uint8_t *d_done, int32_t *d_steps, int32_t out_slots, int32_t chains, void *stream)
+{
+    REQUIRE_ENV(env);
+    if (!d_actions || !d_obs || !d_rewards || !d_done) {
+        mapf_set_error("mapf_env_rollout: NULL buffer");
+        return MAPF_EINVAL;
+    }
+    if (T < 0 || action_slots < 1 || obs_slots < 1 || out_slots < 1 || chains < 0 || chains > MAPF_MAX_CHAINS) {
+        mapf_set_error("mapf_env_rollout: T >= 0, slot counts >= 1 and 0 <= chains <= 16 required");
+        return MAPF_EINVAL;
+    }
+    if (T == 0) return MAPF_OK;
+    const EnvDims &d = env->d;
+    const size_t BN = (size_t)d.B * d.N;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    // The launches of a long rollout repeat with period P = lcm(slot counts): those are captured once per chain into a
+    // graph of P kernel nodes and replayed (one cudaGraphLaunch per chain and period instead of P launches of ~4 us of
+    // host time each, which bound 8 chains at 32 us per step); short rollouts and the tail are launched directly.
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    MAPF_CUDA(cudaStreamIsCapturing(st, &cap));
+    const RolloutPlan pl = rollout_plan(d, T, action_slots, obs_slots, out_slots, chains, cap != cudaStreamCaptureStatusNone);
+    const int S = pl.S, per = pl.per, P = pl.P;
+    const bool graphs = pl.graphs;
+    auto step_t = [&](int t, int e0, int e1, cudaStream_t q) -> int {
+        const size_t sa = (size_t)(t % action_slots), so = (size_t)(t % obs_slots), sr = (size_t)(t % out_slots);
+        return mapf_launch_step_range(env, e0, e1, d_actions + sa * BN, d_obs + so * BN * MAPF_OBS_BYTES_PER_AGENT, d_rewards + sr * BN,
+                                      d_done + sr * d.B, d_steps ? d_steps + sr * d.B : nullptr, q);
+    };
+    if (S == 1) {
+        for (int t = 0; t < T; ++t) {
+            const int rc = step_t(t, 0, d.B, st);
+            if (rc != MAPF_OK) return rc;
+        }
+        return MAPF_OK;
+    }
+    if (!env->chain_fork) MAPF_CUDA(cudaEventCreateWithFlags(&env->chain_fork, cudaEventDisableTiming));
+    for (int j = 0; j < S; ++j) {
+        if (!env->chain_stream[j]) {
+            MAPF_CUDA(cudaStreamCreateWithFlags(&env->chain_stream[j], cudaStreamNonBlocking));
+            MAPF_CUDA(cudaEventCreateWithFlags(&env->chain_done[j], cudaEventDisableTiming));
+        }
+    }
+    // fork: every chain starts after what the caller queued on `stream` (actions ready, earlier readers of the buffers done)
+    MAPF_CUDA(cudaEventRecord(env->chain_fork, st));
+    for (int j = 0; j < S; ++j) MAPF_CUDA(cudaStreamWaitEvent(env->chain_stream[j], env->chain_fork, 0));
+    int rc = MAPF_OK;
+    int t_begin = 0;
+    if (graphs) {
+        mapf_env::RolloutGraph *g = nullptr;
+        const int gen = mapf_step_tuning_generation();
+        for (auto &c : env->rg)
+            if (c.exec[0] && c.act == d_actions && c.obs == d_obs && c.rew == d_rewards && c.done == d_done && c.steps == d_steps &&
+                c.action_slots == action_slots && c.obs_slots == obs_slots && c.out_slots == out_slots && c.S == S && c.P == P &&
+                c.tuning_gen == gen)
+                g = &c;
+        if (!g) {
+            g = &env->rg[env->rg_next];
+            env->rg_next = (env->rg_next + 1) % 2;
+            for (auto &x : g->exec)
+                if (x) {
+                    cudaGraphExecDestroy(x);
+                    x = nullptr;
+                }
+            if (!env->cap_stream) MAPF_CUDA(cudaStreamCreateWithFlags(&env->cap_stream, cudaStreamNonBlocking));
+            for (int j = 0; j < S && rc == MAPF_OK; ++j) {
+                const int e0 = j * per, e1 = e0 + per < d.B ? e0 + per : d.B;
+                cudaGraph_t graph = nullptr;
+                MAPF_CUDA(cudaStreamBeginCapture(env->cap_stream, cudaStreamCaptureModeThreadLocal));
+                for (int t = 0; t < P && rc == MAPF_OK; ++t) rc = step_t(t, e0, e1, env->cap_stream);
+                cudaError_t ce = cudaStreamEndCapture(env->cap_stream, &graph);
+                if (rc == MAPF_OK && ce != cudaSuccess) rc = mapf_cuda_fail(ce, "cudaStreamEndCapture");
+                if (rc == MAPF_OK) {
+                    ce = cudaGraphInstantiate(&g->exec[j], graph, 0);
+                    if (ce != cudaSuccess) rc = mapf_cuda_fail(ce, "cudaGraphInstantiate");
+                }
+                if (graph) cudaGraphDestroy(graph);
+            }
+            if (rc != MAPF_OK) {
+                for (auto &x : g->exec)
+                    if (x) {
+                        cudaGraphExecDestroy(x);
+                        x = nullptr;
+                    }
+            } else {
+                g->act = d_actions, g->obs = d_obs, g->rew = d_rewards, g->done = d_done, g->steps = d_steps;
+                g->action_slots = action_slots, g->obs_slots = obs_slots, g->out_slots = out_slots, g->S = S, g->P = P, g->tuning_gen = gen;
+            }
+        }
+        // period-major issue order: every chain has a period of work queued before any gets its second one
+        for (; rc == MAPF_OK && t_begin + P <= T; t_begin += P)
+            for (int j = 0; j < S && rc == MAPF_OK; ++j) {
+                const cudaError_t ce = cudaGraphLaunch(g->exec[j], env->chain_stream[j]);
+                if (ce != cudaSuccess) rc = mapf_cuda_fail(ce, "cudaGraphLaunch");
+            }
+    }
+    // step-major issue order, so that every chain has work queued from the start; chain j's launch t+1 follows its
+    // launch t by stream order and nothing else
+    for (int t = t_begin; t < T && rc == MAPF_OK; ++t)
+        for (int j = 0; j < S && rc == MAPF_OK; ++j) {
+            const int e0 = j * per, e1 = e0 + per < d.B ? e0 + per : d.B;
+            rc = step_t(t, e0, e1, env->chain_stream[j]);
+        }
+    // join (also after a failed launch: the caller's stream must not run ahead of what was queued)
+    for (int j = 0; j < S; ++j) {
+        cudaError_t e = cudaEventRecord(env->chain_done[j], env->chain_stream[j]);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(st, env->chain_done[j], 0);
+        if (e != cudaSuccess && rc == MAPF_OK) rc = mapf_cuda_fail(e, "mapf_env_rollout join");
+    }
+    return rc;
+}
+
 int mapf_env_step_host(mapf_env *env, const uint8_t *h_actions, uint8_t *h_obs, float *h_rewards, uint8_t *h_done,
                        int32_t *h_steps, uint8_t *d_obs_opt, void *stream)
 {
@@ -342,8 +503,19 @@ int mapf_env_step_host(mapf_env *env, const uint8_t *h_actions, uint8_t *h_obs, 
     for (int i = 0; i < 4; ++i) {
         if (keys[i] != env->hc_key[i]) {
             env->hc_key[i] = keys[i];
-            env->hc_pinned[i] = keys[i] && host_is_pinned(keys[i]);
-            env->hc_alias[i] = env->hc_pinned[i] ? host_device_alias(const_cast<void *>(keys[i])) : nullptr;
+            // an actor that rotates over a few page-locked action buffers pays the two driver queries once per buffer
+            mapf_env::PtrInfo *hit = nullptr;
+            for (auto &c : env->ptr_cache)
+                if (c.key == keys[i] && c.key) hit = &c;
+            if (!hit) {
+                hit = &env->ptr_cache[env->ptr_cache_next];
+                env->ptr_cache_next = (env->ptr_cache_next + 1) % 32;
+                hit->key = keys[i];
+                hit->pinned = keys[i] && host_is_pinned(keys[i]);
+                hit->alias = hit->pinned ? host_device_alias(const_cast<void *>(keys[i])) : nullptr;
+            }
+            env->hc_pinned[i] = hit->pinned;
+            env->hc_alias[i] = hit->alias;
         }
     }
     const bool act_direct = env->hc_pinned[0];
@@ -364,9 +536,17 @@ int mapf_env_step_host(mapf_env *env, const uint8_t *h_actions, uint8_t *h_obs, 
             MAPF_CUDA(cudaEventCreateWithFlags(&env->ev_stepped, cudaEventDisableTiming));
             MAPF_CUDA(cudaEventCreateWithFlags(&env->ev_copied, cudaEventDisableTiming));
         }
-        const uint8_t *act_dev = act_direct ? static_cast<const uint8_t *>(env->hc_alias[0]) : nullptr;  // read in place over PCIe
+        static const bool dma_actions = std::getenv("MAPF_STEP_HOST_DMA_ACTIONS") != nullptr;  // probe: H2D copy node instead
+        const uint8_t *act_dev = act_direct && !dma_actions ? static_cast<const uint8_t *>(env->hc_alias[0]) : nullptr;  // read in place over PCIe
         // issues the whole sequence on `q` (forking to the side stream and joining back)
+        // MAPF_STEP_HOST_TRACE=1 (mode 3 only): timing events between the phases, printed to stderr after the sync
+        static const bool trace = std::getenv("MAPF_STEP_HOST_TRACE") != nullptr;
+        static cudaEvent_t tev[5] = {};
+        const bool tracing = trace && mode == 3;
+        if (tracing && !tev[0])
+            for (auto &e : tev) MAPF_CUDA(cudaEventCreate(&e));
         auto enqueue = [&](cudaStream_t q) -> int {
+            if (tracing) MAPF_CUDA(cudaEventRecord(tev[0], q));
             const uint8_t *a = act_dev;
             if (!a) {
                 MAPF_CUDA(cudaMemcpyAsync(env->d_actions, src_act, BN, cudaMemcpyHostToDevice, q));
@@ -374,17 +554,21 @@ int mapf_env_step_host(mapf_env *env, const uint8_t *h_actions, uint8_t *h_obs, 
             }
             int r = mapf_launch_step_only(env, a, env->d_rewards, env->d_done, env->d_steps_out, q);
             if (r != MAPF_OK) return r;
+            if (tracing) MAPF_CUDA(cudaEventRecord(tev[1], q));
             MAPF_CUDA(cudaEventRecord(env->ev_stepped, q));
             MAPF_CUDA(cudaStreamWaitEvent(env->side_stream, env->ev_stepped, 0));
             MAPF_CUDA(cudaMemcpyAsync(dst_rew, env->d_rewards, BN * 4, cudaMemcpyDeviceToHost, env->side_stream));
             if (dst_steps)
                 MAPF_CUDA(cudaMemcpyAsync(dst_steps, env->d_steps_out, (size_t)d.B * 4, cudaMemcpyDeviceToHost, env->side_stream));
             MAPF_CUDA(cudaMemcpyAsync(dst_done, env->d_done, (size_t)d.B, cudaMemcpyDeviceToHost, env->side_stream));
+            if (tracing) MAPF_CUDA(cudaEventRecord(tev[2], env->side_stream));
             MAPF_CUDA(cudaEventRecord(env->ev_copied, env->side_stream));
             r = mapf_launch_observe(env, obs_dev, nullptr, nullptr, q);
             if (r != MAPF_OK) return r;
+            if (tracing) MAPF_CUDA(cudaEventRecord(tev[3], q));
             if (h_obs) MAPF_CUDA(cudaMemcpyAsync(h_obs, obs_dev, BN * MAPF_OBS_BYTES_PER_AGENT, cudaMemcpyDeviceToHost, q));
             MAPF_CUDA(cudaStreamWaitEvent(q, env->ev_copied, 0));
+            if (tracing) MAPF_CUDA(cudaEventRecord(tev[4], q));
             return MAPF_OK;
         };
         if (mode >= 4) {
@@ -392,12 +576,12 @@ int mapf_env_step_host(mapf_env *env, const uint8_t *h_actions, uint8_t *h_obs, 
             mapf_env::HostGraph *g = nullptr;
             for (auto &c : env->hg)
                 if (c.exec && c.act == src_act && c.rew == dst_rew && c.done == dst_done && c.steps == dst_steps && c.hobs == h_obs &&
-                    c.obs_dev == obs_dev)
+                    c.obs_dev == obs_dev && c.mode == mode)
                     g = &c;
             if (!g) {
                 if (!env->cap_stream) MAPF_CUDA(cudaStreamCreateWithFlags(&env->cap_stream, cudaStreamNonBlocking));
                 g = &env->hg[env->hg_next];
-                env->hg_next = (env->hg_next + 1) % 8;
+                env->hg_next = (env->hg_next + 1) % 32;
                 if (g->exec) {
                     cudaGraphExecDestroy(g->exec);
                     g->exec = nullptr;
@@ -414,7 +598,7 @@ int mapf_env_step_host(mapf_env *env, const uint8_t *h_actions, uint8_t *h_obs, 
                 ce = cudaGraphInstantiate(&g->exec, graph, 0);
                 cudaGraphDestroy(graph);
                 if (ce != cudaSuccess) return mapf_cuda_fail(ce, "cudaGraphInstantiate");
-                g->act = src_act, g->rew = dst_rew, g->done = dst_done, g->steps = dst_steps, g->hobs = h_obs, g->obs_dev = obs_dev;
+                g->act = src_act, g->rew = dst_rew, g->done = dst_done, g->steps = dst_steps, g->hobs = h_obs, g->obs_dev = obs_dev, g->mode = mode;
             }
             MAPF_CUDA(cudaGraphLaunch(g->exec, st));
         } else {
@@ -422,6 +606,12 @@ int mapf_env_step_host(mapf_env *env, const uint8_t *h_actions, uint8_t *h_obs, 
             if (rc != MAPF_OK) return rc;
         }
         MAPF_CUDA(cudaStreamSynchronize(st));
+        if (tracing) {
+            float t[4] = {};
+            for (int i = 0; i < 4; ++i) cudaEventElapsedTime(&t[i], tev[0], tev[i + 1]);
+            std::fprintf(stderr, "step_host trace (us since start): step kernel done %.1f, copies done %.1f, observe done %.1f, joined %.1f\n",
+                         t[0] * 1e3f, t[1] * 1e3f, t[2] * 1e3f, t[3] * 1e3f);
+        }
         if (!out_direct) {
             std::memcpy(h_rewards, pin_rew, BN * 4);
             std::memcpy(h_done, pin_done, (size_t)d.B);

@@ -50,6 +50,17 @@ struct mapf_env {
     uint32_t *navi;
     int32_t *steps;
     int32_t *err;      // latched device error bits
+    // mapf_env_rollout: one internal stream per chain of sub-batch launches, fork / join events
+    cudaStream_t chain_stream[MAPF_MAX_CHAINS];
+    cudaEvent_t chain_done[MAPF_MAX_CHAINS];
+    cudaEvent_t chain_fork;
+    // long rollouts replay, per chain, a captured graph of one slot period (P = lcm of the slot counts) of launches
+    struct RolloutGraph {
+        const void *act, *obs, *rew, *done, *steps;
+        int action_slots, obs_slots, out_slots, S, P, tuning_gen;
+        cudaGraphExec_t exec[MAPF_MAX_CHAINS];
+    } rg[2];
+    int rg_next;
     int split_key, split_per_sm;  // resident CTAs per SM of the split step kernel, cached per (variant) key
     // staging for the host-buffer entry point
     uint8_t *d_actions;
@@ -66,10 +77,17 @@ struct mapf_env {
     // the same sequence captured once per (buffer set, observation target) and replayed with one launch
     struct HostGraph {
         const void *act, *rew, *done, *steps, *hobs, *obs_dev;
+        int mode;
         cudaGraphExec_t exec;
-    } hg[8];
+    } hg[32];
     int hg_next;
     cudaStream_t cap_stream;
+    struct PtrInfo {
+        const void *key;
+        bool pinned;
+        void *alias;
+    } ptr_cache[32];
+    int ptr_cache_next;
     const void *hc_key[4];
     void *hc_alias[4];   // device alias of the page-locked buffer, or NULL
     bool hc_pinned[4];

@@ -41,6 +41,7 @@ struct StepParams {
     int flags;               // MAPF_STEPF_*
     unsigned long long *trace;  // diagnosis: u64[B][16] globaltimer stamps per env (NULL = off), see profiles/step_timeline.py
     int chunks_per_env;      // split form: N * 486 / 16 16-byte output chunks (= 16-bit stream pieces) per env
+    int env_begin, env_end;  // single-role kernel: the launch covers environments [env_begin, env_end) of the batch
 };
 
 enum : int {
@@ -438,7 +439,7 @@ step_observe_kernel(const StepParams p)
     for (int w = lane; w < p.obst_words; w += 32) s_agent[w] = 0;
     __syncwarp();
 
-    for (int e = blockIdx.x * WARPS + warp; e < d.B; e += gridDim.x * WARPS) {
+    for (int e = p.env_begin + blockIdx.x * WARPS + warp; e < p.env_end; e += gridDim.x * WARPS) {
         const size_t env_bytes = (size_t)N * MAPF_OBS_BYTES_PER_AGENT;
         uint8_t *obs_env = p.obs + (size_t)(p.obs_rows ? p.obs_rows[e] : (int64_t)e) * env_bytes;
         const int head = (int)(reinterpret_cast<uintptr_t>(obs_env) & 15);  // bytes before the 16-B boundary
@@ -643,7 +644,7 @@ int launch_step_cfg(const mapf_env *env, StepParams &p, cudaStream_t st)
     }
     if (smem > 48 * 1024)  // per-device attribute; cheap enough to set on every large-smem launch
         MAPF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int grid = (env->d.B + WARPS - 1) / WARPS;
+    int grid = (p.env_end - p.env_begin + WARPS - 1) / WARPS;
     if (tuning().ctas_per_sm > 0) {
         const int cap = env->num_sms * tuning().ctas_per_sm;
         if (grid > cap) grid = cap;
@@ -794,20 +795,30 @@ StepParams make_params(const mapf_env *env)
     p.flags = tuning().flags;
     p.trace = tuning().trace;
     p.chunks_per_env = d.N * MAPF_OBS_BYTES_PER_AGENT / 16;
+    p.env_begin = 0;
+    p.env_end = d.B;
     return p;
 }
 
 }  // namespace
 
+static int g_tuning_generation = 0;
+int mapf_step_tuning_generation() { return g_tuning_generation; }  // captured launches are stale once this moves
+
 void mapf_set_step_tuning(int variant, int flags, int ctas_per_sm)
 {
+    ++g_tuning_generation;
     StepTuning &t = tuning();
     if (variant >= 0) t.variant = variant;
     if (flags >= 0) t.flags = flags;
     if (ctas_per_sm >= 0) t.ctas_per_sm = ctas_per_sm;
 }
 
-void mapf_set_step_trace(unsigned long long *d_trace) { tuning().trace = d_trace; }
+void mapf_set_step_trace(unsigned long long *d_trace)
+{
+    ++g_tuning_generation;
+    tuning().trace = d_trace;
+}
 
 int mapf_launch_step(mapf_env *env, const uint8_t *d_actions, uint8_t *d_obs, const int64_t *d_obs_rows, float *d_rewards,
                      uint8_t *d_done, int32_t *d_steps, cudaStream_t st)
@@ -842,6 +853,22 @@ static int launch_step_only_cfg(mapf_env *env, const StepParams &p, cudaStream_t
     kern<<<(env->d.B + 3) / 4, 128, smem, st>>>(p);
     MAPF_CUDA(cudaGetLastError());
     return MAPF_OK;
+}
+
+// One step of the sub-batch [e0, e1) only (mapf_env_rollout: independent chains of launches over disjoint env ranges);
+// all pointers are those of the whole batch.
+int mapf_launch_step_range(mapf_env *env, int e0, int e1, const uint8_t *d_actions, uint8_t *d_obs, float *d_rewards,
+                           uint8_t *d_done, int32_t *d_steps, cudaStream_t st)
+{
+    StepParams p = make_params(env);
+    p.actions = d_actions;
+    p.obs = d_obs;
+    p.rewards = d_rewards;
+    p.done = d_done;
+    p.steps_out = d_steps;
+    p.env_begin = e0;
+    p.env_end = e1;
+    return launch_step<true>(env, p, st);
 }
 
 int mapf_launch_step_only(mapf_env *env, const uint8_t *d_actions, float *d_rewards, uint8_t *d_done, int32_t *d_steps,

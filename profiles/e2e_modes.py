@@ -18,6 +18,8 @@ env.reset(seed=0, density=0.3)
 ring = torch.empty((4, B, N, 6, 9, 9), dtype=torch.uint8, device="cuda")
 rng = np.random.default_rng(0)
 acts = rng.integers(0, 5, size=(16, B, N)).astype(np.uint8)
+if os.environ.get("E2E_PINNED_ACTIONS", "1") != "0":   # page-locked action buffers handed over in place (no staging copy)
+    acts = torch.as_tensor(acts).pin_memory()
 steps = int(sys.argv[1]) if len(sys.argv) > 1 else 200
 for s in range(10):
     env.step_host(acts[s % 16], device_obs=ring[s % 4])
@@ -43,7 +45,8 @@ for s in range(50):
 print(f"   GPU span median {np.median(spans):.1f} us, wall median {np.median(walls) * 1e6:.1f} us (includes the two event records)")
 # host-side cost of the call path alone: copy of the actions into the pinned buffer
 hb = env.host_actions
+acts_np = acts.numpy() if isinstance(acts, torch.Tensor) else acts
 t0 = time.perf_counter()
 for s in range(200):
-    np.copyto(hb, acts[s % 16])
+    np.copyto(hb, acts_np[s % 16])
 print(f"   np.copyto of the actions: {(time.perf_counter() - t0) / 200 * 1e6:.1f} us")

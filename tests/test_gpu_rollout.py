@@ -1,0 +1,209 @@
+"""GPU parity of mapf_env_rollout (T scripted steps as independent sub-batch chains on internal streams): the same
+golden traces from the live reference, the C oracle on seeded inputs, and a twin handle stepped one launch at a
+time.  Bit-exact for every chain count, ragged sub-batches and cyclic output rings."""
+import hashlib
+
+import numpy as np
+import pytest
+
+from helpers import golden, instances, random_instance
+from oracle import oracle
+
+pytestmark = pytest.mark.gpu
+
+
+def sha8(b):
+    return np.frombuffer(hashlib.sha256(b).digest()[:8], dtype=np.uint64)[0]
+
+
+def make_env(B, N, L):
+    from mapf_rl_b200 import BatchedEnvironment
+    return BatchedEnvironment(B, N, L)
+
+
+@pytest.mark.parametrize("N,chains", [(16, 0), (32, 3), (64, 2)])
+@pytest.mark.parametrize("stream", ["U", "G"])
+def test_golden_traces_through_rollout(N, stream, chains):
+    """The traces recorded from the live reference (tests/golden/make_golden.py), all steps in ONE rollout call."""
+    import torch
+    z = golden("traces.npz")
+    maps, agents, goals = instances(N)
+    pre = f"n{N}_{stream}_"
+    ks = z[pre + "instances"]
+    env = make_env(len(ks), N, 40)
+    env.load(maps[ks], agents[ks], goals[ks])
+    acts = torch.as_tensor(np.ascontiguousarray(z[pre + "actions"].transpose(1, 0, 2))).cuda()  # [T,B,N]
+    T = acts.shape[0]
+    obs, rew, done, steps = env.rollout(acts, chains=chains)
+    obs, rew, done, steps = obs.cpu().numpy(), rew.cpu().numpy(), done.cpu().numpy(), steps.cpu().numpy()
+    for s in range(T):
+        for q in range(len(ks)):
+            assert np.array_equal(rew[s, q], z[pre + "rewards"][q, s]), (q, s)
+            assert done[s, q] == z[pre + "done"][q, s]
+            assert sha8(obs[s, q].tobytes()) == z[pre + "obs_sha8"][q, s + 1], (q, s)
+        assert np.array_equal(steps[s], np.full(len(ks), s + 1))
+    assert np.array_equal(env.agents_pos.cpu().numpy(), z[pre + "pos"][:, T])
+    env.check()
+
+
+@pytest.mark.parametrize("B,N,L,chains", [(37, 20, 24, 1), (37, 20, 24, 2), (37, 20, 24, 5), (37, 20, 24, 16),
+                                          (3, 8, 12, 4), (130, 40, 40, 7), (64, 96, 56, 3)])
+def test_rollout_vs_oracle_and_twin(B, N, L, chains):
+    """Ragged sub-batches (B not a multiple of chains or of 4), K > 1 agent slots, cyclic rings shorter than T."""
+    import torch
+    rng = np.random.default_rng(B * 1000 + N + chains)
+    insts = [random_instance(rng, L, N, 0.25) for _ in range(B)]
+    maps = np.stack([i[0] for i in insts])
+    agents = np.stack([i[1] for i in insts])
+    goals = np.stack([i[2] for i in insts])
+    T, A, R, S = 11, 4, 3, 5
+    acts = rng.integers(0, 5, size=(A, B, N)).astype(np.uint8)
+    env, twin = make_env(B, N, L), make_env(B, N, L)
+    env.load(maps, agents, goals)
+    twin.load(maps, agents, goals)
+    dev = env.device
+    obs_ring = torch.zeros((R, B, N, 6, 9, 9), dtype=torch.uint8, device=dev)
+    rew_ring = torch.zeros((S, B, N), dtype=torch.float32, device=dev)
+    done_ring = torch.zeros((S, B), dtype=torch.uint8, device=dev)
+    steps_ring = torch.zeros((S, B), dtype=torch.int32, device=dev)
+    d_acts = torch.as_tensor(acts).to(dev)
+    env.rollout(d_acts, num_steps=T, out_obs=obs_ring, out_rewards=rew_ring, out_done=done_ring, out_steps=steps_ring,
+                chains=chains)
+    # twin: one launch per step, keeping what the rings must hold at the end
+    exp_obs, exp_rew, exp_done = {}, {}, {}
+    n_or = min(B, 6)
+    ora = []
+    for k in range(n_or):
+        o = oracle.OracleEnv()
+        o.load(maps[k], agents[k], goals[k])
+        ora.append(o)
+    for t in range(T):
+        o, r, d = twin.step(d_acts[t % A])
+        exp_obs[t % R], exp_rew[t % S], exp_done[t % S] = o.clone(), r.clone(), d.clone()
+        on, rn, dn = o.cpu().numpy(), r.cpu().numpy(), d.cpu().numpy()
+        for k in range(n_or):
+            (oo, _), orw, od, _ = ora[k].step(acts[t % A, k])
+            assert np.array_equal(oo.astype(np.uint8), on[k]), (t, k)
+            assert np.array_equal(np.asarray(orw, dtype=np.float32), rn[k]), (t, k)
+            assert bool(od) == bool(dn[k])
+    for s in range(R):
+        assert torch.equal(obs_ring[s], exp_obs[s]), s
+    for s in range(S):
+        assert torch.equal(rew_ring[s], exp_rew[s]), s
+        assert torch.equal(done_ring[s], exp_done[s]), s
+        last_t = max(t for t in range(T) if t % S == s)
+        assert torch.equal(steps_ring[s], torch.full((B,), last_t + 1, dtype=torch.int32, device=dev))
+    assert torch.equal(env.agents_pos, twin.agents_pos)
+    assert torch.equal(env.steps, twin.steps)
+    env.check()
+    twin.check()
+
+
+def test_rollout_then_step_and_reset_interleave():
+    """A rollout joins back into the caller's stream: a plain step / masked reset / observe queued right after it
+    sees its results, and a second rollout continues from them."""
+    import torch
+    B, N, L = 96, 32, 40
+    env, twin = make_env(B, N, L), make_env(B, N, L)
+    for e in (env, twin):
+        e.reset(seed=5, density=0.3)
+    g = torch.Generator(device="cuda")
+    g.manual_seed(1)
+    acts = torch.randint(0, 5, (6, B, N), generator=g, device="cuda", dtype=torch.uint8)
+    env.rollout(acts[:3], chains=4)
+    for t in range(3):
+        twin.step(acts[t])
+    o1, r1, d1 = env.step(acts[3])
+    o2, r2, d2 = twin.step(acts[3])
+    assert torch.equal(o1, o2) and torch.equal(r1, r2) and torch.equal(d1, d2)
+    mask = (torch.arange(B, device="cuda") % 3 == 0).to(torch.uint8)
+    env.reset(mask=mask, seed=9, density=0.3)
+    twin.reset(mask=mask, seed=9, density=0.3)
+    ob, rw, dn, st = env.rollout(acts[4:], chains=3)
+    for t in (4, 5):
+        o2, r2, d2 = twin.step(acts[t])
+        assert torch.equal(ob[t - 4], o2) and torch.equal(rw[t - 4], r2) and torch.equal(dn[t - 4], d2)
+    assert torch.equal(env.observe()[0], twin.observe()[0])
+    assert torch.equal(env.steps, twin.steps)
+    env.check()
+
+
+def test_rollout_full_size_equals_single_launch_steps():
+    """BASELINE configs[1] size (8192 x 32, 40 x 40): 12 steps as 4 and as 8 chains equal 12 whole-batch launches."""
+    import torch
+    B, N, L, T = 8192, 32, 40, 12
+    g = torch.Generator(device="cuda")
+    g.manual_seed(3)
+    acts = torch.randint(0, 5, (T, B, N), generator=g, device="cuda", dtype=torch.uint8)
+    ref = make_env(B, N, L)
+    ref.reset(seed=11, density=0.3)
+    exp = [tuple(x.clone() for x in ref.step(acts[t])) for t in range(T)]
+    for chains in (4, 8):
+        env = make_env(B, N, L)
+        env.reset(seed=11, density=0.3)
+        obs, rew, done, steps = env.rollout(acts, chains=chains)
+        for t in range(T):
+            assert torch.equal(obs[t], exp[t][0]), (chains, t)
+            assert torch.equal(rew[t], exp[t][1]) and torch.equal(done[t], exp[t][2])
+        assert torch.equal(env.agents_pos, ref.agents_pos)
+        assert int(steps[-1].min()) == T and int(steps[-1].max()) == T
+        env.check()
+        env.close()
+        del obs
+
+
+@pytest.mark.parametrize("chains", [0, 3])
+def test_rollout_long_enough_for_graph_replay(chains):
+    """T >= 4 slot periods on >= 2048 envs: whole periods are replayed from per-chain captured graphs (twice, so the
+    second call hits the cache), the tail is launched directly; different rings afterwards rebuild the graphs."""
+    import torch
+    B, N, L = 2050, 8, 16
+    env, twin = make_env(B, N, L), make_env(B, N, L)
+    for e in (env, twin):
+        e.reset(seed=21, density=0.2)
+    g = torch.Generator(device="cuda")
+    g.manual_seed(2)
+    A, R, S, T = 3, 2, 1, 29     # period lcm(3, 2, 1) = 6: 4 periods replayed + 5 direct steps
+    acts = torch.randint(0, 5, (A, B, N), generator=g, device="cuda", dtype=torch.uint8)
+    rings = [tuple(torch.zeros(sh, dtype=dt, device="cuda") for sh, dt in
+                   (((R, B, N, 6, 9, 9), torch.uint8), ((S, B, N), torch.float32), ((S, B), torch.uint8), ((S, B), torch.int32)))
+             for _ in range(2)]
+    t_glob = 0
+    for rnd, ring in enumerate((rings[0], rings[0], rings[1])):
+        obs, rew, done, steps = ring
+        env.rollout(acts, num_steps=T, out_obs=obs, out_rewards=rew, out_done=done, out_steps=steps, chains=chains)
+        exp = {}
+        for t in range(T):
+            o, r, d = twin.step(acts[t % A])
+            exp[t % R] = o.clone()
+            t_glob += 1
+        for s in range(R):
+            assert torch.equal(obs[s], exp[s]), (rnd, s)
+        assert torch.equal(rew[0], r) and torch.equal(done[0], d)
+        assert torch.equal(env.agents_pos, twin.agents_pos)
+        assert torch.equal(env.steps, twin.steps)
+    env.check()
+
+
+def test_rollout_bad_arguments():
+    import ctypes as C
+    import torch
+    from mapf_rl_b200 import _native
+    env = make_env(8, 4, 10)
+    env.reset(seed=0, density=0.2)
+    acts = torch.zeros((2, 8, 4), dtype=torch.uint8, device="cuda")
+    obs = torch.empty((2, 8, 4, 6, 9, 9), dtype=torch.uint8, device="cuda")
+    rew = torch.empty((2, 8, 4), dtype=torch.float32, device="cuda")
+    done = torch.empty((2, 8), dtype=torch.uint8, device="cuda")
+    lib, vp = _native.lib(), C.c_void_p
+    ok = (vp(acts.data_ptr()), 2, vp(obs.data_ptr()), 2, vp(rew.data_ptr()), vp(done.data_ptr()), None, 2)
+    assert lib.mapf_env_rollout(env._h, 0, *ok, 0, None) == 0          # T = 0: nothing to do
+    assert lib.mapf_env_rollout(env._h, 2, *ok, 17, None) == _native.MAPF_EINVAL
+    assert lib.mapf_env_rollout(env._h, -1, *ok, 0, None) == _native.MAPF_EINVAL
+    assert lib.mapf_env_rollout(env._h, 2, None, 2, *ok[2:], 0, None) == _native.MAPF_EINVAL
+    assert lib.mapf_env_rollout(env._h, 2, ok[0], 0, *ok[2:], 0, None) == _native.MAPF_EINVAL
+    # an out-of-range action latches like in step (environment.py:289-290)
+    acts[1, 3, 2] = 7
+    env.rollout(acts, chains=2)
+    with pytest.raises(AssertionError):
+        env.check()
