@@ -87,8 +87,19 @@ def env_config(torch, out, name, B, N, L, steps=200):
         coll = float((rew == -0.5).float().mean().item())
         env.check()
         ach = algo_bytes(N, L) * B * N / (us * 1e-6) / 1e9
+        # the same stream through mapf_env_rollout (independent sub-batch chains, graph replay)
+        T = 640
+        rr = torch.empty((2, B, N), dtype=torch.float32, device=dev)
+        rd = torch.empty((2, B), dtype=torch.uint8, device=dev)
+        rs = torch.empty((2, B), dtype=torch.int32, device=dev)
+        roll = lambda: env.rollout(acts, num_steps=T, out_obs=replay, out_rewards=rr, out_done=rd, out_steps=rs)
+        us_roll = ev_time(torch, roll, 2, warm=1) / T
+        plan = env.rollout_plan(T, 16, R, 2)
+        env.check()
         out({"config": name, "stream": stream, "num_envs": B, "num_agents": N, "map_length": L, "us_per_step": round(us, 2),
              "agent_steps_per_s": B * N / (us * 1e-6), "roofline_frac_of_measured_hbm": ach / peak,
+             "us_per_step_rollout": round(us_roll, 2), "rollout_chains": plan[0], "rollout_agent_steps_per_s": B * N / (us_roll * 1e-6),
+             "rollout_roofline_frac": algo_bytes(N, L) * B * N / (us_roll * 1e-6) / 1e9 / peak,
              "collision_fraction_last_step": coll})
     out({"config": name, "what": "reset = device generator + BFS heuristic maps, all envs", "num_envs": B, "num_agents": N,
          "map_length": L, "us_per_reset_batch": round(t_reset, 1), "envs_reset_per_s": B / (t_reset * 1e-6),
