@@ -309,6 +309,34 @@ def test_step_host_every_mode(mode, pinned):
         lib.mapf_debug_step_host_mode(prev)
 
 
+def test_step_host_results_are_fresh_when_the_call_returns():
+    """Many back-to-back mapf_env_step_host calls (graph replay over rotating page-locked action buffers and observation
+    slots) at a size where the result copies take tens of microseconds: the host rewards / done / steps read right after
+    each call are those of THAT step (a twin stepped on the device), the device observation that of the last."""
+    import torch
+    B, N, L, T = 4096, 32, 40, 120
+    env, twin = make_env(B, N, L), make_env(B, N, L)
+    for e in (env, twin):
+        e.reset(seed=17, density=0.3)
+    g = torch.Generator(device="cuda")
+    g.manual_seed(5)
+    acts = torch.randint(0, 5, (T, B, N), generator=g, device="cuda", dtype=torch.uint8)
+    acts_host = acts.cpu().pin_memory()
+    exp = []
+    for t in range(T):
+        o, r, d = twin.step(acts[t])
+        exp.append((r.cpu().numpy().copy(), d.cpu().numpy().copy()))
+    ring = torch.zeros((2, B, N, 6, 9, 9), dtype=torch.uint8, device="cuda")
+    for t in range(T):
+        _, rew, done, steps = env.step_host(acts_host[t], device_obs=ring[t % 2])
+        assert np.array_equal(rew, exp[t][0]), t
+        assert np.array_equal(done, exp[t][1]), t
+        assert int(steps.min()) == t + 1 and int(steps.max()) == t + 1
+    assert torch.equal(ring[(T - 1) % 2], o)          # stream-ordered read of the last device observation
+    assert torch.equal(env.agents_pos, twin.agents_pos)
+    env.check()
+
+
 def test_step_host_pageable_caller_buffers():
     """mapf_env_step_host with ordinary (pageable) numpy buffers goes through the handle's pinned staging area."""
     import ctypes as C
