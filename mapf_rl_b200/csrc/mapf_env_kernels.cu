@@ -7,6 +7,8 @@
 //
 // None of this is a dense contraction: no tensor cores.  K1+K2 is bound by the HBM write of the
 // observation bytes (486 B per agent-step); everything else stays in shared memory / registers.
+#include <type_traits>
+
 #include "mapf_common.cuh"
 
 namespace {
@@ -108,7 +110,17 @@ bfs_navi_kernel(EnvDims d, const int32_t *__restrict__ env_ids, const uint8_t *_
                 if (fro[q][w]) dist[gx * d.L + gy] = 0;
     }
 
-    for (int t = 1;; ++t) {
+    // Wavefront loop.  Adjacent reachable cells of a 4-connected grid differ by exactly one in distance, so "the
+    // neighbour is strictly closer" (environment.py:260-274) is "its distance mod 3 is mine minus one": the loop only
+    // records WHICH residue a cell's wave had (m1 / m2; residue 0 = reached and in neither) -- one LOP per word and wave
+    // instead of four plane updates -- and the four planes are derived once at the end.
+    uint32_t m1[RPL][RW], m2[RPL][RW];
+#pragma unroll
+    for (int q = 0; q < RPL; ++q)
+#pragma unroll
+        for (int w = 0; w < RW; ++w) m1[q][w] = m2[q][w] = 0;
+    auto wave = [&](auto selc, const int t) -> bool {
+        constexpr int sel = decltype(selc)::value;  // t mod 3
         uint32_t nw[RPL][RW];
         uint32_t any = 0;
 #pragma unroll
@@ -127,20 +139,18 @@ bfs_navi_kernel(EnvDims d, const int32_t *__restrict__ env_ids, const uint8_t *_
                 const uint32_t dn = q < RPL - 1 ? fro[q < RPL - 1 ? q + 1 : q][w] : below;
                 const uint32_t x = (fl | fr | up | dn) & unv[q][w];
                 nw[q][w] = x;
-                pl[0][q][w] |= x & up;  // neighbour x-1 (row above) is closer   environment.py:260
-                pl[1][q][w] |= x & dn;  // neighbour x+1                          environment.py:264
-                pl[2][q][w] |= x & fl;  // neighbour y-1                          environment.py:268
-                pl[3][q][w] |= x & fr;  // neighbour y+1                          environment.py:272
                 any |= x;
             }
         }
-        if (!__any_sync(MAPF_FULL_MASK, any != 0)) break;
+        if (!__any_sync(MAPF_FULL_MASK, any != 0)) return false;
 #pragma unroll
         for (int q = 0; q < RPL; ++q)
 #pragma unroll
             for (int w = 0; w < RW; ++w) {
                 unv[q][w] &= ~nw[q][w];
                 fro[q][w] = nw[q][w];
+                if constexpr (sel == 1) m1[q][w] |= nw[q][w];
+                if constexpr (sel == 2) m2[q][w] |= nw[q][w];
                 if (dist) {
                     uint32_t x = nw[q][w];
                     while (x) {
@@ -150,6 +160,60 @@ bfs_navi_kernel(EnvDims d, const int32_t *__restrict__ env_ids, const uint8_t *_
                     }
                 }
             }
+        return true;
+    };
+    for (int t = 1;; t += 3) {
+        if (!wave(std::integral_constant<int, 1>{}, t)) break;
+        if (!wave(std::integral_constant<int, 2>{}, t + 1)) break;
+        if (!wave(std::integral_constant<int, 0>{}, t + 2)) break;
+    }
+
+    // The four heuristic planes from the residues: with z = reached cells of residue 0, direction "neighbour n is
+    // closer" holds at a cell c iff (c in m1, n in z) or (c in m2, n in m1) or (c in z, n in m2).
+    {
+        uint32_t z[RPL][RW];
+#pragma unroll
+        for (int q = 0; q < RPL; ++q) {
+            const int row = lane * RPL + q;
+#pragma unroll
+            for (int w = 0; w < RW; ++w) {
+                int lo = max(4 - 32 * w, 0), hi = min(d.L + 4 - 32 * w, 32);
+                uint32_t cm = 0;
+                if (hi > lo) cm = (hi - lo == 32) ? 0xffffffffu : (((1u << (hi - lo)) - 1u) << lo);
+                const uint32_t fre = (row < d.L) ? (~__ldg(ob + (row + 4) * d.RWS + w) & cm) : 0u;
+                z[q][w] = fre & ~unv[q][w] & ~m1[q][w] & ~m2[q][w];
+            }
+        }
+        auto closer = [](uint32_t c1, uint32_t c2, uint32_t cz, uint32_t n1, uint32_t n2, uint32_t nz) -> uint32_t {
+            return (c1 & nz) | (c2 & n1) | (cz & n2);
+        };
+#pragma unroll
+        for (int w = 0; w < RW; ++w) {
+            // residue rows of the neighbouring lanes that touch this lane's block
+            uint32_t a1 = __shfl_up_sync(MAPF_FULL_MASK, m1[RPL - 1][w], 1), b1 = __shfl_down_sync(MAPF_FULL_MASK, m1[0][w], 1);
+            uint32_t a2 = __shfl_up_sync(MAPF_FULL_MASK, m2[RPL - 1][w], 1), b2 = __shfl_down_sync(MAPF_FULL_MASK, m2[0][w], 1);
+            uint32_t az = __shfl_up_sync(MAPF_FULL_MASK, z[RPL - 1][w], 1), bz = __shfl_down_sync(MAPF_FULL_MASK, z[0][w], 1);
+            if (lane == 0) a1 = a2 = az = 0;
+            if (lane == 31) b1 = b2 = bz = 0;
+#pragma unroll
+            for (int q = 0; q < RPL; ++q) {
+                auto left = [&](const uint32_t(&m)[RPL][RW]) {  // bit y <- bit y-1
+                    return w > 0 ? __funnelshift_l(m[q][w > 0 ? w - 1 : 0], m[q][w], 1) : m[q][w] << 1;
+                };
+                auto right = [&](const uint32_t(&m)[RPL][RW]) {  // bit y <- bit y+1
+                    return w < RW - 1 ? __funnelshift_r(m[q][w], m[q][w < RW - 1 ? w + 1 : w], 1) : m[q][w] >> 1;
+                };
+                const uint32_t c1 = m1[q][w], c2 = m2[q][w], cz = z[q][w];
+                const uint32_t u1 = q > 0 ? m1[q > 0 ? q - 1 : 0][w] : a1, u2 = q > 0 ? m2[q > 0 ? q - 1 : 0][w] : a2,
+                               uz = q > 0 ? z[q > 0 ? q - 1 : 0][w] : az;
+                const uint32_t d1 = q < RPL - 1 ? m1[q < RPL - 1 ? q + 1 : q][w] : b1, d2 = q < RPL - 1 ? m2[q < RPL - 1 ? q + 1 : q][w] : b2,
+                               dz = q < RPL - 1 ? z[q < RPL - 1 ? q + 1 : q][w] : bz;
+                pl[0][q][w] = closer(c1, c2, cz, u1, u2, uz);                       // neighbour x-1   environment.py:260
+                pl[1][q][w] = closer(c1, c2, cz, d1, d2, dz);                       // neighbour x+1   environment.py:264
+                pl[2][q][w] = closer(c1, c2, cz, left(m1), left(m2), left(z));      // neighbour y-1   environment.py:268
+                pl[3][q][w] = closer(c1, c2, cz, right(m1), right(m2), right(z));   // neighbour y+1   environment.py:272
+            }
+        }
     }
 
     // emit the overlapping 16x16 tiles (mapf_common.cuh): a map row is padded row pr = row + 4, which is
