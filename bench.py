@@ -323,6 +323,10 @@ def run_ours(args):
                              "api": "same call with the full observation tensor also copied to host (drop-in Environment.step)"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "kernel": "step_observe_kernel<RW=2,K=1,DO_STEP,4 warps,12 CTAs/SM>",
+                         "per_launch": {"algorithmic_bytes": algo_bytes(N, L) * per * N, "avg_duration_us": per_launch_s * 1e6,
+                                        "concurrent_launches": chains,
+                                        "note": "each chain's K launches run back to back for the whole timed region, so a launch "
+                                                "lasts one step period while sharing the GPU with the other chains' launches"},
                          "achieved_is": "algorithmic bytes of one whole-batch step / step period in the timed region (the "
                                         f"{chains} sub-batch launches of a step overlap those of its neighbours); `traffic` is "
                                         "the ncu DRAM bytes of a whole-batch launch",
