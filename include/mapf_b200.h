@@ -151,7 +151,8 @@ int mapf_env_step_host(mapf_env *env, const uint8_t *h_actions, uint8_t *h_obs, 
 
 /* Diagnostics / tuning (process-wide; profiles/step_variants.py, tests): selects the step kernel form.
  *   variant     >= 10: split producer/consumer kernel (10 = default shape, 11..17 other warp splits);
- *               0..3: single-role kernel (CTA shapes);  < 0 leaves the current value
+ *               0..9: single-role kernel; 1 (default) picks the CTA shape per launch, the others force one (see
+ *               launch_step_rwk in mapf_step_kernels.cu);  < 0 leaves the current value
  *   flags       MAPF_STEPF_* bit set of mapf_step_kernels.cu (1 = L2 evict_last on heuristic-map loads); < 0 keeps
  *   ctas_per_sm cap on resident CTAs per SM (0 = as many as fit); < 0 keeps
  * The same three values are read once from MAPF_STEP_VARIANT / MAPF_STEP_FLAGS / MAPF_STEP_CTAS_PER_SM. */

@@ -732,11 +732,22 @@ template <int RW, int K, bool DO_STEP>
 int launch_step_rwk(const mapf_env *env, StepParams &p, cudaStream_t st)
 {
     if constexpr (RW == 2 && K == 1 && DO_STEP) {
-        switch (tuning().variant) {
+        // CTA shape / register budget of the hot geometry (40x40, <= 32 agents), measured at 8192 x 32 (profiles/
+        // r1_rollout_cta_shapes.log; us per step as one whole-batch launch / as 8 rollout chains):
+        //   0: 8 warps, 48 regs, 40 warps/SM   33.3 / 24.9        7: 8 warps, 64 regs, 32 warps/SM   34.8 / 24.2
+        //   4: 4 warps, 40 regs, 48 warps/SM   34.3 / 25.7        8: 4 warps, 64 regs, 32 warps/SM   34.6 / 24.4
+        //   2: 4 warps, 32 regs (spills)       38.1 / 32.9        3: 2 warps, 32 regs                 38.1 / 32.2
+        // 1 (default) picks 0 for a launch over the whole batch and 7 for a sub-batch launch of mapf_env_rollout, whose
+        // concurrent chains supply the parallelism that the extra resident warps otherwise would.
+        int v = tuning().variant;
+        if (v == 1) v = (p.env_end - p.env_begin < env->d.B) ? 7 : 0;
+        switch (v) {
             case 0: return launch_step_cfg<RW, K, DO_STEP, 8, 5>(env, p, st);
             case 2: return launch_step_cfg<RW, K, DO_STEP, 4, 16>(env, p, st);
             case 3: return launch_step_cfg<RW, K, DO_STEP, 2, 32>(env, p, st);
-            default: break;
+            case 7: return launch_step_cfg<RW, K, DO_STEP, 8, 4>(env, p, st);
+            case 8: return launch_step_cfg<RW, K, DO_STEP, 4, 8>(env, p, st);
+            default: break;  // 4: the general shape below
         }
     }
     return launch_step_cfg<RW, K, DO_STEP, 4, (K == 1 ? 12 : 1)>(env, p, st);
