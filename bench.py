@@ -279,7 +279,10 @@ def run_ours(args):
 
     e2e_steps = max(10, min(args.steps, 400))
     e2e_run(3, False)
-    e2e_value = e2e_run(e2e_steps, False)
+    # the host side of this path (Python, graph launch, stream sync) is sensitive to what else runs on the box: three
+    # repetitions, the median is reported and all three are kept in the JSON line
+    e2e_reps = sorted(e2e_run(e2e_steps, False) for _ in range(3))
+    e2e_value = e2e_reps[1]
     e2e_run(1, True)
     e2e_obs_value = e2e_run(max(3, min(args.steps, 20)), True)
 
@@ -316,7 +319,7 @@ def run_ours(args):
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * N, "d2h_bytes_per_step": B * N * 4 + B * 5,
                     "api": "mapf_env_step_host on one of 16 page-locked action buffers (read in place over PCIe) -> step kernel -> observe kernel || "
                            "D2H rewards/done/steps on a side stream -> sync (one CUDA-graph launch); observations stay in "
-                           "the device replay ring (north star)", "steps": e2e_steps,
+                           "the device replay ring (north star)", "steps": e2e_steps, "repetitions": e2e_reps,
                     "host_mode": os.environ.get("MAPF_STEP_HOST_MODE", "4")},
             "e2e_host_obs": {"value": e2e_obs_value, "unit": UNIT, "h2d_bytes_per_step": B * N,
                              "d2h_bytes_per_step": B * N * 4 + B * 5 + B * N * 486,
