@@ -731,7 +731,7 @@ int launch_split(mapf_env *env, const StepParams &p, cudaStream_t st)
 template <int RW, int K, bool DO_STEP>
 int launch_step_rwk(const mapf_env *env, StepParams &p, cudaStream_t st)
 {
-    if constexpr (RW == 2 && K == 1 && DO_STEP) {
+    if constexpr (RW == 2 && K == 1) {
         // CTA shape / register budget of the hot geometry (40x40, <= 32 agents), measured at 8192 x 32 (profiles/
         // r1_rollout_cta_shapes.log; us per step as one whole-batch launch / as 8 rollout chains):
         //   0: 8 warps, 48 regs, 40 warps/SM   33.3 / 24.9        7: 8 warps, 64 regs, 32 warps/SM   34.8 / 24.2
