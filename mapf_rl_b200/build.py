@@ -7,7 +7,10 @@ import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
-LIB_PATH = os.path.join(_HERE, "libmapf_b200.so")
+# MAPF_B200_LIB points the package at another build of the library (A/B runs of two builds on one GPU box); such a
+# library is used as it is, never rebuilt
+LIB_OVERRIDE = os.environ.get("MAPF_B200_LIB")
+LIB_PATH = LIB_OVERRIDE or os.path.join(_HERE, "libmapf_b200.so")
 SOURCES = ["mapf_abi.cu", "mapf_env_kernels.cu", "mapf_step_kernels.cu", "mapf_reset_kernels.cu", "mapf_per_kernels.cu", "mapf_replay_kernels.cu"]
 HEADERS = ["mapf_common.cuh", os.path.join("..", "..", "include", "mapf_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -22,6 +25,8 @@ def _nvcc() -> str:
 
 
 def is_stale() -> bool:
+    if LIB_OVERRIDE:
+        return False
     if not os.path.exists(LIB_PATH):
         return True
     t = os.path.getmtime(LIB_PATH)

@@ -60,18 +60,24 @@ __global__ void pack_load_kernel(EnvDims d, const int32_t *__restrict__ env_ids,
 // exactly "this cell is new in wave t and that neighbour was in the frontier of wave t-1", so the
 // four direction planes fall out of the same step and no distance array is needed.
 // ---------------------------------------------------------------------------------------------
-template <int RW, int RPL>
-__global__ void __launch_bounds__(kBfsWarps * 32)
+// APW agents share a warp (LW = 32 / APW lanes each): maps of up to 48 rows fit 16 lanes x 3 rows, so two agents' waves
+// run in one instruction stream (at 40x40 one agent per warp leaves 12 of 32 lanes idle); the warp iterates until
+// both are done.
+template <int RW, int RPL, int APW>
+__global__ void __launch_bounds__(kBfsWarps * 32, RW * RPL <= 9 ? 8 : 1)  // <= 64 registers (32 resident warps per SM)
+                                                                          // wherever that does not spill
 bfs_navi_kernel(EnvDims d, const int32_t *__restrict__ env_ids, const uint8_t *__restrict__ env_mask, int n,
                 const uint32_t *__restrict__ obst, const uint8_t *__restrict__ goal, uint32_t *__restrict__ navi,
                 int32_t *__restrict__ dist_out)
 {
-    const int lane = lane_id();
-    const int g = blockIdx.x * kBfsWarps + (threadIdx.x >> 5);
-    if (g >= n * d.N) return;
-    const int i = g / d.N, a = g - i * d.N;
+    constexpr int LW = 32 / APW;
+    const int lane = lane_id() % LW;             // lane within the agent's group
+    const int g = (blockIdx.x * kBfsWarps + (threadIdx.x >> 5)) * APW + lane_id() / LW;
+    bool alive = g < n * d.N;
+    const int i = alive ? g / d.N : 0, a = alive ? g - i * d.N : 0;
     const int e = env_ids ? env_ids[i] : i;
-    if (env_mask && !env_mask[e]) return;  // masked re-computation after a device-side reset
+    if (alive && env_mask && !env_mask[e]) alive = false;  // masked re-computation after a device-side reset
+    if (!__any_sync(MAPF_FULL_MASK, alive)) return;
     const uint32_t *ob = obst + (size_t)e * d.obst_stride;
 
     // unv = free and not yet visited, fro = frontier of the previous wave, pl = the four heuristic planes
@@ -79,7 +85,7 @@ bfs_navi_kernel(EnvDims d, const int32_t *__restrict__ env_ids, const uint8_t *_
     const int gx = goal[((size_t)e * d.N + a) * 2], gy = goal[((size_t)e * d.N + a) * 2 + 1];
 #pragma unroll
     for (int q = 0; q < RPL; ++q) {
-        const int row = lane * RPL + q;
+        const int row = alive ? lane * RPL + q : d.L;  // a group without an agent owns no rows
 #pragma unroll
         for (int w = 0; w < RW; ++w) {
             // in-map column mask for this word: padded bits [4, L+4)
@@ -95,11 +101,11 @@ bfs_navi_kernel(EnvDims d, const int32_t *__restrict__ env_ids, const uint8_t *_
         }
     }
 
-    int32_t *dist = dist_out ? dist_out + ((size_t)i * d.N + a) * d.L * d.L : nullptr;
-    if (dist) {
+    int32_t *dist = (dist_out && alive) ? dist_out + ((size_t)i * d.N + a) * d.L * d.L : nullptr;
+    if (dist_out) {
         for (int q = 0; q < RPL; ++q) {
             const int row = lane * RPL + q;
-            if (row < d.L)
+            if (dist && row < d.L)
                 for (int y = 0; y < d.L; ++y) dist[row * d.L + y] = MAPF_DIST_UNREACHABLE;
         }
         __syncwarp();
@@ -107,7 +113,7 @@ bfs_navi_kernel(EnvDims d, const int32_t *__restrict__ env_ids, const uint8_t *_
         for (int q = 0; q < RPL; ++q)
 #pragma unroll
             for (int w = 0; w < RW; ++w)
-                if (fro[q][w]) dist[gx * d.L + gy] = 0;
+                if (dist && fro[q][w]) dist[gx * d.L + gy] = 0;
     }
 
     // Wavefront loop.  Adjacent reachable cells of a 4-connected grid differ by exactly one in distance, so "the
@@ -126,10 +132,10 @@ bfs_navi_kernel(EnvDims d, const int32_t *__restrict__ env_ids, const uint8_t *_
 #pragma unroll
         for (int w = 0; w < RW; ++w) {
             // rows of the neighbouring lanes that touch this lane's block
-            uint32_t above = __shfl_up_sync(MAPF_FULL_MASK, fro[RPL - 1][w], 1);
-            uint32_t below = __shfl_down_sync(MAPF_FULL_MASK, fro[0][w], 1);
+            uint32_t above = __shfl_up_sync(MAPF_FULL_MASK, fro[RPL - 1][w], 1, LW);
+            uint32_t below = __shfl_down_sync(MAPF_FULL_MASK, fro[0][w], 1, LW);
             if (lane == 0) above = 0;
-            if (lane == 31) below = 0;
+            if (lane == LW - 1) below = 0;
 #pragma unroll
             for (int q = 0; q < RPL; ++q) {
                 const uint32_t f = fro[q][w];
@@ -151,8 +157,8 @@ bfs_navi_kernel(EnvDims d, const int32_t *__restrict__ env_ids, const uint8_t *_
                 fro[q][w] = nw[q][w];
                 if constexpr (sel == 1) m1[q][w] |= nw[q][w];
                 if constexpr (sel == 2) m2[q][w] |= nw[q][w];
-                if (dist) {
-                    uint32_t x = nw[q][w];
+                if (dist_out) {  // a kernel argument: the loop is compiled twice, the common one without any of this
+                    uint32_t x = dist ? nw[q][w] : 0u;
                     while (x) {
                         int b = __ffs(x) - 1;
                         x &= x - 1;
@@ -174,7 +180,7 @@ bfs_navi_kernel(EnvDims d, const int32_t *__restrict__ env_ids, const uint8_t *_
         uint32_t z[RPL][RW];
 #pragma unroll
         for (int q = 0; q < RPL; ++q) {
-            const int row = lane * RPL + q;
+            const int row = alive ? lane * RPL + q : d.L;
 #pragma unroll
             for (int w = 0; w < RW; ++w) {
                 int lo = max(4 - 32 * w, 0), hi = min(d.L + 4 - 32 * w, 32);
@@ -190,11 +196,11 @@ bfs_navi_kernel(EnvDims d, const int32_t *__restrict__ env_ids, const uint8_t *_
 #pragma unroll
         for (int w = 0; w < RW; ++w) {
             // residue rows of the neighbouring lanes that touch this lane's block
-            uint32_t a1 = __shfl_up_sync(MAPF_FULL_MASK, m1[RPL - 1][w], 1), b1 = __shfl_down_sync(MAPF_FULL_MASK, m1[0][w], 1);
-            uint32_t a2 = __shfl_up_sync(MAPF_FULL_MASK, m2[RPL - 1][w], 1), b2 = __shfl_down_sync(MAPF_FULL_MASK, m2[0][w], 1);
-            uint32_t az = __shfl_up_sync(MAPF_FULL_MASK, z[RPL - 1][w], 1), bz = __shfl_down_sync(MAPF_FULL_MASK, z[0][w], 1);
+            uint32_t a1 = __shfl_up_sync(MAPF_FULL_MASK, m1[RPL - 1][w], 1, LW), b1 = __shfl_down_sync(MAPF_FULL_MASK, m1[0][w], 1, LW);
+            uint32_t a2 = __shfl_up_sync(MAPF_FULL_MASK, m2[RPL - 1][w], 1, LW), b2 = __shfl_down_sync(MAPF_FULL_MASK, m2[0][w], 1, LW);
+            uint32_t az = __shfl_up_sync(MAPF_FULL_MASK, z[RPL - 1][w], 1, LW), bz = __shfl_down_sync(MAPF_FULL_MASK, z[0][w], 1, LW);
             if (lane == 0) a1 = a2 = az = 0;
-            if (lane == 31) b1 = b2 = bz = 0;
+            if (lane == LW - 1) b1 = b2 = bz = 0;
 #pragma unroll
             for (int q = 0; q < RPL; ++q) {
                 auto left = [&](const uint32_t(&m)[RPL][RW]) {  // bit y <- bit y-1
@@ -222,7 +228,7 @@ bfs_navi_kernel(EnvDims d, const int32_t *__restrict__ env_ids, const uint8_t *_
 #pragma unroll
     for (int q = 0; q < RPL; ++q) {
         const int row = lane * RPL + q;
-        if (row >= d.L) continue;
+        if (row >= d.L || !alive) continue;
         const int pr = row + 4, bx1 = pr >> 3, r1 = pr & 7;
 #pragma unroll
         for (int by = 0; by < 4 * RW; ++by) {
@@ -346,15 +352,36 @@ template <int RW>
 static int launch_bfs_rw(mapf_env *env, const int32_t *ids, const uint8_t *mask, int n, int32_t *dist, cudaStream_t st)
 {
     const EnvDims &d = env->d;
-    const int rpl = (d.L + 31) / 32;
-    const long warps = (long)n * d.N;
+    const int apw = d.L <= 48 ? 2 : 1;       // two agents per warp while the map fits 16 lanes x 3 rows
+    const int rpl = (d.L + 32 / apw - 1) / (32 / apw);
+    const long warps = ((long)n * d.N + apw - 1) / apw;
     const int grid = (int)((warps + kBfsWarps - 1) / kBfsWarps);
-    switch (rpl) {
-        case 1: bfs_navi_kernel<RW, 1><<<grid, kBfsWarps * 32, 0, st>>>(d, ids, mask, n, env->obst, env->goal, env->navi, dist); break;
-        case 2: bfs_navi_kernel<RW, 2><<<grid, kBfsWarps * 32, 0, st>>>(d, ids, mask, n, env->obst, env->goal, env->navi, dist); break;
-        case 3: bfs_navi_kernel<RW, 3><<<grid, kBfsWarps * 32, 0, st>>>(d, ids, mask, n, env->obst, env->goal, env->navi, dist); break;
-        case 4: bfs_navi_kernel<RW, 4><<<grid, kBfsWarps * 32, 0, st>>>(d, ids, mask, n, env->obst, env->goal, env->navi, dist); break;
-        default: mapf_set_error("unsupported map size"); return MAPF_EINVAL;
+#define MAPF_BFS_LAUNCH(RPL, APW) \
+    bfs_navi_kernel<RW, RPL, APW><<<grid, kBfsWarps * 32, 0, st>>>(d, ids, mask, n, env->obst, env->goal, env->navi, dist)
+    bool ok = true;
+    if (apw == 2) {
+        if constexpr (RW <= 2) {
+            switch (rpl) {
+                case 1: MAPF_BFS_LAUNCH(1, 2); break;
+                case 2: MAPF_BFS_LAUNCH(2, 2); break;
+                case 3: MAPF_BFS_LAUNCH(3, 2); break;
+                default: ok = false;
+            }
+        } else ok = false;
+    } else {
+        if constexpr (RW >= 2) {
+            switch (rpl) {
+                case 2: MAPF_BFS_LAUNCH(2, 1); break;
+                case 3: MAPF_BFS_LAUNCH(3, 1); break;
+                case 4: MAPF_BFS_LAUNCH(4, 1); break;
+                default: ok = false;
+            }
+        } else ok = false;
+    }
+#undef MAPF_BFS_LAUNCH
+    if (!ok) {
+        mapf_set_error("unsupported map size");
+        return MAPF_EINVAL;
     }
     MAPF_CUDA(cudaGetLastError());
     return MAPF_OK;
