@@ -750,6 +750,14 @@ int launch_step_rwk(const mapf_env *env, StepParams &p, cudaStream_t st)
             default: break;  // 4: the general shape below
         }
     }
+    if constexpr (K == 2 && DO_STEP) {
+        // two agents per lane (33..64 agents): the general shape below runs at 80 registers / 24 warps per SM.  Capped at
+        // 64 registers (32 warps per SM, no spills) a whole-batch launch of 8192 x 64 agents takes 69.2 instead of 72.7 us;
+        // the rollout's sub-batch launches are no faster (52.8 vs 52.4 us per step; profiles/r1_rollout_cta_shapes.log)
+        int v = tuning().variant;
+        if (v == 1) v = (p.env_end - p.env_begin < env->d.B) ? 4 : 9;
+        if (v == 9) return launch_step_cfg<RW, K, DO_STEP, 4, 8>(env, p, st);
+    }
     return launch_step_cfg<RW, K, DO_STEP, 4, (K == 1 ? 12 : 1)>(env, p, st);
 }
 
