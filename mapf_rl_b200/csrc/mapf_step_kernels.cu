@@ -750,7 +750,7 @@ int launch_step_rwk(const mapf_env *env, StepParams &p, cudaStream_t st)
             default: break;  // 4: the general shape below
         }
     }
-    if constexpr (K == 2 && DO_STEP) {
+    if constexpr (K == 2 && DO_STEP && RW <= 2) {  // (at 80x80 shared memory holds 20 warps per SM and the cap costs 1.4 %)
         // two agents per lane (33..64 agents): the general shape below runs at 80 registers / 24 warps per SM.  Capped at
         // 64 registers (32 warps per SM, no spills) a whole-batch launch of 8192 x 64 agents takes 69.2 instead of 72.7 us;
         // the rollout's sub-batch launches are no faster (52.8 vs 52.4 us per step; profiles/r1_rollout_cta_shapes.log)
