@@ -278,7 +278,7 @@ def run_ours(args):
         return world * B * N * steps / el
 
     e2e_steps = max(10, min(args.steps, 400))
-    e2e_run(3, False)
+    e2e_run(2 * A, False)   # warm-up: every (action buffer, observation slot) pair has its captured launch sequence
     # the host side of this path (Python, graph launch, stream sync) is sensitive to what else runs on the box: three
     # repetitions, the median is reported and all three are kept in the JSON line
     e2e_reps = sorted(e2e_run(e2e_steps, False) for _ in range(3))
