@@ -211,6 +211,7 @@ def run_ours(args):
     g.manual_seed(args.seed + rank)
     actions = torch.randint(0, 5, (A, B, N), generator=g, device=dev, dtype=torch.uint8)
     actions_host = actions.cpu().pin_memory()  # [A,B,N] page-locked: step_host hands slot s % A to the GPU in place
+    actions_host = [actions_host[i] for i in range(A)]
 
     def barrier():
         if world > 1:
@@ -268,11 +269,13 @@ def run_ours(args):
     ms_single = sharding.max_over_ranks(ev2.elapsed_time(ev3), dev)
 
     # ---- e2e: through the host-buffer C-ABI entry point (mapf_env_step_host) ---------------------
+    replay_slots = [replay[i] for i in range(R)]
+
     def e2e_run(steps, want_obs):
         barrier()
         t0 = time.perf_counter()
         for s in range(steps):
-            env.step_host(actions_host[s % A], want_obs=want_obs, device_obs=replay[s % R])
+            env.step_host(actions_host[s % A], want_obs=want_obs, device_obs=replay_slots[s % R])
         torch.cuda.synchronize(dev)
         el = sharding.max_over_ranks(time.perf_counter() - t0, dev)
         return world * B * N * steps / el

@@ -235,8 +235,14 @@ class BatchedEnvironment:
             # a page-locked uint8 CPU tensor (torch pin_memory) is read by the GPU in place: no staging copy
             assert (actions.device.type == "cpu" and actions.dtype == torch.uint8 and actions.is_contiguous()
                     and tuple(actions.shape) == (B, N)), "actions number"
-            if actions.is_pinned():
-                pa = C.c_void_p(actions.data_ptr())
+            ptr = actions.data_ptr()
+            known = hb.setdefault("pinned_ptrs", {})   # is_pinned() is a driver query: once per buffer
+            if ptr not in known:
+                if len(known) > 64:
+                    known.clear()
+                known[ptr] = C.c_void_p(ptr) if actions.is_pinned() else None
+            if known[ptr] is not None:
+                pa = known[ptr]
             else:
                 np.copyto(hb["actions_np"], actions.numpy())
         elif actions is not hb["actions_np"]:   # the caller may fill env.host_actions in place instead
