@@ -311,7 +311,7 @@ def run_ours(args):
                              f"({R * B * N * 486 / 1e6:.0f} MB) + {env.arena_bytes / 1e6:.0f} MB state arena, both > 126 MB L2",
                        "extra_warmup": "0.3 s of untimed steps after W so SM clocks are under load"},
             "clocks": clocks,
-            "gpu_launches": args.steps * chains,
+            "gpu_launches": args.steps * chains if chains else 1,
             "launch": {"api": "mapf_env_rollout (one call for the K steps)", "chains": chains, "envs_per_chain": per,
                        "graph_period_steps": graph_period,
                        "note": "each step of the batch = `chains` launches of step_observe_kernel over disjoint env ranges on "

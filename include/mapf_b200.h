@@ -117,6 +117,10 @@ int mapf_env_observe_rows(mapf_env *env, uint8_t *d_obs_base, const int64_t *d_o
  *   d_actions u8[action_slots, B, N]   d_obs u8[obs_slots, B, N, 6, 9, 9]
  *   d_rewards f32[out_slots, B, N]     d_done u8[out_slots, B]     d_steps i32[out_slots, B] (optional)
  * Environments are independent (no reference code path couples two Environment objects), so the batch runs as `chains`
+ * With chains = 0 on the hot geometry (maps of 25..56 cells, up to 32 agents, B >= 2048, T >= 16) the rollout is ONE launch of
+ * a persistent kernel: every resident warp takes its environments through all T steps, one environment after another, so
+ * nothing is launched between steps, the warps drift out of phase on their own and an environment's heuristic lines are re-read
+ * from L1 / L2 (22.3 us per step at 8192 x 32 agents).  Otherwise the batch runs as `chains`
  * contiguous sub-batches (1..MAPF_MAX_CHAINS; 0 = default: 1 below 2048 environments, else 4, or 8 when the rollout is long
  * enough to be replayed from graphs), each an independent chain of T launches on a stream of its own: launch t+1 of a chain
  * waits for launch t of THAT chain only, the chains drift out of phase, and the observation stores of one overlap the
@@ -131,7 +135,8 @@ int mapf_env_rollout(mapf_env *env, int32_t T, const uint8_t *d_actions, int32_t
                      int32_t chains, void *stream);
 
 /* How mapf_env_rollout would run these arguments: number of chains, environments per chain, and the number of steps per
- * replayed graph (0 = every step launched directly).  Outputs are optional. */
+ * replayed graph (0 = every step launched directly).  chains_out = 0 means the persistent kernel: one launch for the whole
+ * rollout.  Outputs are optional. */
 int mapf_env_rollout_plan(mapf_env *env, int32_t T, int32_t action_slots, int32_t obs_slots, int32_t out_slots,
                           int32_t chains, int32_t *chains_out, int32_t *envs_per_chain_out, int32_t *graph_period_out);
 
@@ -157,6 +162,10 @@ int mapf_env_step_host(mapf_env *env, const uint8_t *h_actions, uint8_t *h_obs, 
  *   ctas_per_sm cap on resident CTAs per SM (0 = as many as fit); < 0 keeps
  * The same three values are read once from MAPF_STEP_VARIANT / MAPF_STEP_FLAGS / MAPF_STEP_CTAS_PER_SM. */
 int mapf_debug_step_tuning(int32_t variant, int32_t flags, int32_t ctas_per_sm);
+/* Knobs of the persistent kernel behind mapf_env_rollout (process-wide; < 0 keeps a value): persistent 0 = never use it,
+ * envs_per_warp = environments each resident warp takes through their T steps (0 = automatic), cta_warps = 1, 2 or 4.
+ * Read once from MAPF_ROLLOUT_PERSISTENT / MAPF_ROLLOUT_ENVS_PER_WARP / MAPF_ROLLOUT_CTA_WARPS. */
+int mapf_debug_rollout_tuning(int32_t persistent, int32_t envs_per_warp, int32_t cta_warps);
 /* Selects the form of mapf_env_step_host (0..4, see there; < 0 only queries); returns the mode in force. */
 int mapf_debug_step_host_mode(int32_t mode);
 /* Diagnosis: while d_trace != NULL (u64[B, 16], device) the split step kernel stamps %globaltimer per environment:

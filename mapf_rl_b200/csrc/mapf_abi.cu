@@ -15,6 +15,8 @@ int mapf_launch_step(mapf_env *, const uint8_t *, uint8_t *, const int64_t *, fl
 int mapf_launch_observe(mapf_env *, uint8_t *, const int64_t *, uint8_t *, cudaStream_t);
 int mapf_launch_step_only(mapf_env *, const uint8_t *, float *, uint8_t *, int32_t *, cudaStream_t);
 int mapf_launch_step_range(mapf_env *, int, int, const uint8_t *, uint8_t *, float *, uint8_t *, int32_t *, cudaStream_t);
+int mapf_launch_rollout_persistent(mapf_env *, int, const uint8_t *, int, uint8_t *, int, float *, uint8_t *, int32_t *, int, int,
+                                   int, cudaStream_t);
 void mapf_set_step_tuning(int, int, int);
 int mapf_step_tuning_generation();
 void mapf_set_step_trace(unsigned long long *);
@@ -321,6 +323,32 @@ struct RolloutPlan {
     int S, per, P;
     bool graphs;
 };
+// Process-wide knobs of the persistent rollout kernel (mapf_debug_rollout_tuning; read once from the environment):
+//   MAPF_ROLLOUT_PERSISTENT=0      never use it (chains of launches instead)
+//   MAPF_ROLLOUT_ENVS_PER_WARP=n   environments each resident warp takes through their T steps (0 = B / (24 warps per SM))
+//   MAPF_ROLLOUT_CTA_WARPS=1|2|4   warps per CTA
+struct RolloutTuning {
+    int persistent, envs_per_warp, cta_warps;
+};
+RolloutTuning &rollout_tuning()
+{
+    static RolloutTuning t = [] {
+        RolloutTuning r{1, 0, 4};
+        if (const char *s = std::getenv("MAPF_ROLLOUT_PERSISTENT")) r.persistent = std::atoi(s);
+        if (const char *s = std::getenv("MAPF_ROLLOUT_ENVS_PER_WARP")) r.envs_per_warp = std::atoi(s);
+        if (const char *s = std::getenv("MAPF_ROLLOUT_CTA_WARPS")) r.cta_warps = std::atoi(s);
+        return r;
+    }();
+    return t;
+}
+bool rollout_persistent_enabled() { return rollout_tuning().persistent != 0; }
+// the persistent kernel serves the default request (chains = 0) on the hot geometry when the rollout is long enough for its
+// environment-major order to fill the GPU
+bool rollout_uses_persistent(const EnvDims &d, int T, int chains)
+{
+    return rollout_persistent_enabled() && chains == 0 && d.RW == 2 && d.K == 1 && d.B >= 2048 && T >= 16;
+}
+
 RolloutPlan rollout_plan(const EnvDims &d, int T, int action_slots, int obs_slots, int out_slots, int chains, bool capturing)
 {
     auto gcd = [](int a, int b) { while (b) { int r = a % b; a = b; b = r; } return a; };
@@ -345,6 +373,12 @@ int mapf_env_rollout_plan(mapf_env *env, int32_t T, int32_t action_slots, int32_
         mapf_set_error("mapf_env_rollout_plan: T >= 0, slot counts >= 1 and 0 <= chains <= 16 required");
         return MAPF_EINVAL;
     }
+    if (rollout_uses_persistent(env->d, T, chains)) {  // one launch for the whole rollout
+        if (chains_out) *chains_out = 0;
+        if (envs_per_chain_out) *envs_per_chain_out = env->d.B;
+        if (graph_period_out) *graph_period_out = 0;
+        return MAPF_OK;
+    }
     const RolloutPlan pl = rollout_plan(env->d, T, action_slots, obs_slots, out_slots, chains, false);
     if (chains_out) *chains_out = pl.S;
     if (envs_per_chain_out) *envs_per_chain_out = pl.per;
@@ -368,6 +402,11 @@ int mapf_env_rollout(mapf_env *env, int32_t T, const uint8_t *d_actions, int32_t
     const EnvDims &d = env->d;
     const size_t BN = (size_t)d.B * d.N;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (rollout_uses_persistent(d, T, chains)) {
+        const int rc = mapf_launch_rollout_persistent(env, T, d_actions, action_slots, d_obs, obs_slots, d_rewards, d_done, d_steps,
+                                                      out_slots, rollout_tuning().envs_per_warp, rollout_tuning().cta_warps, st);
+        if (rc != MAPF_EINVAL) return rc;
+    }
     // The launches of a long rollout repeat with period P = lcm(slot counts): those are captured once per chain into a
     // graph of P kernel nodes and replayed (one cudaGraphLaunch per chain and period instead of P launches of ~4 us of
     // host time each, which bound 8 chains at 32 us per step); short rollouts and the tail are launched directly.
@@ -674,6 +713,15 @@ int mapf_env_step_host(mapf_env *env, const uint8_t *h_actions, uint8_t *h_obs, 
 int mapf_debug_step_tuning(int32_t variant, int32_t flags, int32_t ctas_per_sm)
 {
     mapf_set_step_tuning(variant, flags, ctas_per_sm);
+    return MAPF_OK;
+}
+
+int mapf_debug_rollout_tuning(int32_t persistent, int32_t envs_per_warp, int32_t cta_warps)
+{
+    RolloutTuning &t = rollout_tuning();
+    if (persistent >= 0) t.persistent = persistent;
+    if (envs_per_warp >= 0) t.envs_per_warp = envs_per_warp;
+    if (cta_warps >= 0) t.cta_warps = cta_warps;
     return MAPF_OK;
 }
 

@@ -413,6 +413,41 @@ __device__ __forceinline__ void clear_agent_bits(uint32_t *s_agent, const EnvReg
     __syncwarp();
 }
 
+// Expand the env's bit stream (1 bit -> 1 bool byte) and write its N*486-byte observation block: 16 bytes per lane per
+// store, fully coalesced streaming stores; `head` = bytes between the 16-byte boundary below obs_env and obs_env.
+__device__ __forceinline__ void expand_store_block(const StepParams &p, uint8_t *obs_env, const int head, const size_t env_bytes,
+                                                   const uint32_t *s_bits, const int lane, const bool obs_policy,
+                                                   const uint64_t pol_stream)
+{
+    const int total = head + (int)env_bytes;
+    const int c_lo = (head + 15) >> 4, c_hi = total >> 4;  // chunks [c_lo, c_hi) are whole
+    uint8_t *obase = obs_env - head;                       // 16-byte aligned
+    const uint16_t *S16 = reinterpret_cast<const uint16_t *>(s_bits);
+#pragma unroll 4
+    for (int c = c_lo + lane; c < c_hi; c += 32) {
+        const uint32_t s = S16[c];
+        uint4 v;
+        v.x = expand4(s & 0xfu);
+        v.y = expand4((s >> 4) & 0xfu);
+        v.z = expand4((s >> 8) & 0xfu);
+        v.w = expand4(s >> 12);
+        uint4 *dst = reinterpret_cast<uint4 *>(obase + (c << 4));
+        if (p.flags & MAPF_STEPF_DIAG_NO_STORE) {
+            if (v.x == 0xdeadbeefu) __stcs(dst, v);  // never true: keeps the expansion alive
+        } else if (obs_policy) stg_policy(dst, v, pol_stream);
+        else __stcs(dst, v);
+    }
+    // ragged first / last chunk of an unaligned observation block
+    if ((head != 0 && lane == 0) || ((total & 15) != 0 && lane == 1)) {
+        const int c = lane == 0 ? 0 : c_hi;
+        const uint32_t s = S16[c];
+        for (int b = 0; b < 16; ++b) {
+            const int g = (c << 4) + b;
+            if (g >= head && g < total) obase[g] = (uint8_t)((s >> b) & 1u);
+        }
+    }
+}
+
 // ---- K1+K2, single-role form: every warp steps an env, then expands and stores its own observation block.
 // Kept for observe(), unaligned observation bases and agent counts that are not a multiple of 8.
 template <int RW, int K, bool DO_STEP, int WARPS, int MINB>
@@ -446,38 +481,66 @@ step_observe_kernel(const StepParams p)
         EnvRegs<K> r;
         env_step_gather<RW, K, DO_STEP>(p, e, lane, s_obst, s_agent, s_bits, s_tgt, s_cell, head, pol_keep, r);
 
-        // expand 1 bit -> 1 bool byte, 16 bytes per lane per store, fully coalesced streaming stores
-        {
-            const int total = head + (int)env_bytes;
-            const int c_lo = (head + 15) >> 4, c_hi = total >> 4;  // chunks [c_lo, c_hi) are whole
-            uint8_t *obase = obs_env - head;                       // 16-byte aligned
-            const uint16_t *S16 = reinterpret_cast<const uint16_t *>(s_bits);
-#pragma unroll 4
-            for (int c = c_lo + lane; c < c_hi; c += 32) {
-                const uint32_t s = S16[c];
-                uint4 v;
-                v.x = expand4(s & 0xfu);
-                v.y = expand4((s >> 4) & 0xfu);
-                v.z = expand4((s >> 8) & 0xfu);
-                v.w = expand4(s >> 12);
-                uint4 *dst = reinterpret_cast<uint4 *>(obase + (c << 4));
-                if (p.flags & MAPF_STEPF_DIAG_NO_STORE) {
-                    if (v.x == 0xdeadbeefu) __stcs(dst, v);  // never true: keeps the expansion alive
-                } else if (obs_policy) stg_policy(dst, v, pol_stream);
-                else __stcs(dst, v);
-            }
-            // ragged first / last chunk of an unaligned observation block
-            if ((head != 0 && lane == 0) || ((total & 15) != 0 && lane == 1)) {
-                const int c = lane == 0 ? 0 : c_hi;
-                const uint32_t s = S16[c];
-                for (int b = 0; b < 16; ++b) {
-                    const int g = (c << 4) + b;
-                    if (g >= head && g < total) obase[g] = (uint8_t)((s >> b) & 1u);
-                }
-            }
-        }
+        expand_store_block(p, obs_env, head, env_bytes, s_bits, lane, obs_policy, pol_stream);
         __syncwarp();
         clear_agent_bits<RW, K>(s_agent, r);  // the agent bits this env set
+    }
+}
+
+// ---- K1+K2 for a scripted rollout, persistent form: a warp takes an environment through ALL T steps before it moves to its
+// next one.  Nothing is launched between steps, the warps drift out of phase on their own, and what an environment re-reads
+// every step (its agents' heuristic tile lines -- an agent changes tile once in ~12 steps --, goals, the obstacle bitmap) is
+// re-read by the same SM a few microseconds later and comes from L1 / L2 instead of DRAM.
+struct RolloutArgs {
+    int T, action_slots, obs_slots, out_slots;
+    const uint8_t *actions;  // [action_slots, B, N]
+    uint8_t *obs;            // [obs_slots, B, N, 6, 9, 9]
+    float *rewards;          // [out_slots, B, N]
+    uint8_t *done;           // [out_slots, B]
+    int32_t *steps_out;      // [out_slots, B] or NULL
+};
+
+template <int RW, int K, int WARPS, int MINB>
+__global__ void __launch_bounds__(WARPS * 32, MINB)
+step_rollout_kernel(const StepParams p0, const RolloutArgs r)
+{
+    extern __shared__ __align__(16) uint32_t smem[];
+    const EnvDims &d = p0.d;
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int N = d.N;
+    uint32_t *s_obst = smem + (size_t)warp * p0.warp_smem_words;
+    uint32_t *s_agent = s_obst + p0.obst_words;
+    uint32_t *s_bits = s_agent + p0.obst_words;
+    uint16_t *s_tgt = reinterpret_cast<uint16_t *>(s_bits + p0.bits_words);
+    uint16_t *s_cell = s_tgt + 32 * K;
+    const uint64_t pol_keep = l2_policy_evict_last();
+    const uint64_t pol_stream = l2_policy_evict_first();
+    const bool obs_policy = p0.flags & MAPF_STEPF_OBS_POLICY;
+    for (int w = lane; w < p0.obst_words; w += 32) s_agent[w] = 0;
+    __syncwarp();
+    const size_t BN = (size_t)d.B * N;
+    const size_t env_bytes = (size_t)N * MAPF_OBS_BYTES_PER_AGENT;
+    for (int e = p0.env_begin + blockIdx.x * WARPS + warp; e < p0.env_end; e += gridDim.x * WARPS) {
+        int sa = 0, so = 0, sr = 0;  // t % slots without a division per step
+        for (int t = 0; t < r.T; ++t) {
+            StepParams p = p0;
+            p.actions = r.actions + (size_t)sa * BN;
+            p.obs = r.obs + (size_t)so * BN * MAPF_OBS_BYTES_PER_AGENT;
+            p.rewards = r.rewards + (size_t)sr * BN;
+            p.done = r.done + (size_t)sr * d.B;
+            p.steps_out = r.steps_out ? r.steps_out + (size_t)sr * d.B : nullptr;
+            uint8_t *obs_env = p.obs + (size_t)e * env_bytes;
+            const int head = (int)(reinterpret_cast<uintptr_t>(obs_env) & 15);
+            EnvRegs<K> regs;
+            env_step_gather<RW, K, true>(p, e, lane, s_obst, s_agent, s_bits, s_tgt, s_cell, head, pol_keep, regs);
+            expand_store_block(p, obs_env, head, env_bytes, s_bits, lane, obs_policy, pol_stream);
+            __syncwarp();
+            clear_agent_bits<RW, K>(s_agent, regs);
+            if (++sa == r.action_slots) sa = 0;
+            if (++so == r.obs_slots) so = 0;
+            if (++sr == r.out_slots) sr = 0;
+        }
     }
 }
 
@@ -888,6 +951,44 @@ int mapf_launch_step_range(mapf_env *env, int e0, int e1, const uint8_t *d_actio
     p.env_begin = e0;
     p.env_end = e1;
     return launch_step<true>(env, p, st);
+}
+
+// Persistent rollout (see step_rollout_kernel): only the hot geometry (maps up to 56 cells, up to 32 agents) is instantiated;
+// MAPF_EINVAL tells the caller to use chains of launches instead.
+template <int WARPS>
+static int launch_rollout_persistent_cfg(mapf_env *env, const StepParams &p, const RolloutArgs &r, int epw, cudaStream_t st)
+{
+    auto kern = step_rollout_kernel<2, 1, WARPS, 32 / WARPS>;   // 64 registers
+    const size_t smem = (size_t)p.warp_smem_words * 4 * WARPS;
+    if (smem > 48 * 1024) MAPF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int warps = (env->d.B + epw - 1) / epw;
+    const int grid = (warps + WARPS - 1) / WARPS;
+    kern<<<grid, WARPS * 32, smem, st>>>(p, r);
+    MAPF_CUDA(cudaGetLastError());
+    return MAPF_OK;
+}
+
+int mapf_launch_rollout_persistent(mapf_env *env, int T, const uint8_t *d_actions, int action_slots, uint8_t *d_obs, int obs_slots,
+                                   float *d_rewards, uint8_t *d_done, int32_t *d_steps, int out_slots, int envs_per_warp, int cta_warps,
+                                   cudaStream_t st)
+{
+    if (env->d.RW != 2 || env->d.K != 1) return MAPF_EINVAL;
+    StepParams p = make_params(env);
+    RolloutArgs r{T, action_slots, obs_slots, out_slots, d_actions, d_obs, d_rewards, d_done, d_steps};
+    // Every warp of the (fully resident) grid takes the same number of environments through their T steps, one after another.
+    // Measured at 8192 x 32 agents (profiles/r1_rollout_persistent.log; us per step): 2 environments per warp 24.5, 3: 22.3,
+    // 4: 23.7, 6: 28.5, 8: 33.7 with 4-warp CTAs; 2-warp CTAs 22.6 / 22.3 at 3 / 4; 1-warp CTAs 25.9 / 28.0.  About 18 resident
+    // warps per SM: few enough for their environments' heuristic lines to stay in L1, enough to keep DRAM busy.
+    int epw = envs_per_warp;
+    if (epw <= 0) {
+        const int capacity = env->num_sms * 24;
+        epw = (env->d.B + capacity - 1) / capacity;
+    }
+    switch (cta_warps) {
+        case 1: return launch_rollout_persistent_cfg<1>(env, p, r, epw, st);
+        case 2: return launch_rollout_persistent_cfg<2>(env, p, r, epw, st);
+        default: return launch_rollout_persistent_cfg<4>(env, p, r, epw, st);
+    }
 }
 
 int mapf_launch_step_only(mapf_env *env, const uint8_t *d_actions, float *d_rewards, uint8_t *d_done, int32_t *d_steps,

@@ -185,6 +185,95 @@ def test_rollout_long_enough_for_graph_replay(chains):
     env.check()
 
 
+@pytest.fixture
+def rollout_tuning():
+    """Sets the knobs of the persistent rollout kernel for one test and restores the defaults afterwards."""
+    from mapf_rl_b200 import _native
+    lib = _native.lib()
+    yield lambda persistent=-1, envs_per_warp=-1, cta_warps=-1: lib.mapf_debug_rollout_tuning(persistent, envs_per_warp, cta_warps)
+    lib.mapf_debug_rollout_tuning(1, 0, 4)
+
+
+@pytest.mark.parametrize("N,L,epw,cta_warps", [(20, 30, 0, 4), (20, 30, 3, 4), (32, 40, 5, 2), (7, 25, 2, 1), (32, 56, 4, 4)])
+def test_rollout_persistent_kernel(rollout_tuning, N, L, epw, cta_warps):
+    """chains = 0 on the hot geometry (maps of 25..56 cells, <= 32 agents, >= 2048 envs, T >= 16): ONE launch of the persistent
+    kernel, every warp taking `epw` environments through all T steps.  Ragged last warp / CTA, agent counts whose blocks are
+    not 16-byte aligned, cyclic rings shorter than T; bit-exact against a twin stepped launch by launch and, for the first
+    environments, against the oracle."""
+    import torch
+    B, T, A, R, S = 2051, 19, 3, 2, 2
+    rollout_tuning(1, epw, cta_warps)
+    env, twin = make_env(B, N, L), make_env(B, N, L)
+    for e in (env, twin):
+        e.reset(seed=31 + N, density=0.25)
+    assert env.rollout_plan(T, A, R, S)[0] == 0          # the persistent kernel takes it
+    g = torch.Generator(device="cuda")
+    g.manual_seed(7)
+    acts = torch.randint(0, 5, (A, B, N), generator=g, device="cuda", dtype=torch.uint8)
+    obs = torch.zeros((R, B, N, 6, 9, 9), dtype=torch.uint8, device="cuda")
+    rew = torch.zeros((S, B, N), dtype=torch.float32, device="cuda")
+    done = torch.zeros((S, B), dtype=torch.uint8, device="cuda")
+    steps = torch.zeros((S, B), dtype=torch.int32, device="cuda")
+    maps, pos0, goals = env.map.cpu().numpy(), env.agents_pos.cpu().numpy(), env.goals_pos.cpu().numpy()
+    env.rollout(acts, num_steps=T, out_obs=obs, out_rewards=rew, out_done=done, out_steps=steps)
+    ora = []
+    for k in (0, 1, B - 1):
+        o = oracle.OracleEnv()
+        o.load(maps[k], pos0[k], goals[k])
+        ora.append((k, o))
+    exp_obs, exp_rew, exp_done = {}, {}, {}
+    a_host = acts.cpu().numpy()
+    for t in range(T):
+        o, r, d = twin.step(acts[t % A])
+        exp_obs[t % R], exp_rew[t % S], exp_done[t % S] = o.clone(), r.clone(), d.clone()
+        for k, oe in ora:
+            (oo, _), orw, od, _ = oe.step(a_host[t % A, k])
+            assert np.array_equal(oo.astype(np.uint8), o[k].cpu().numpy()), (t, k)
+            assert np.array_equal(np.asarray(orw, dtype=np.float32), r[k].cpu().numpy()), (t, k)
+    for s in range(R):
+        assert torch.equal(obs[s], exp_obs[s]), s
+    for s in range(S):
+        assert torch.equal(rew[s], exp_rew[s]) and torch.equal(done[s], exp_done[s]), s
+        last_t = max(t for t in range(T) if t % S == s)
+        assert torch.equal(steps[s], torch.full((B,), last_t + 1, dtype=torch.int32, device="cuda"))
+    assert torch.equal(env.agents_pos, twin.agents_pos) and torch.equal(env.steps, twin.steps)
+    # a plain step right after it sees the rollout's state; the chained form gives the same results
+    o1, r1, d1 = env.step(acts[0])
+    o2, r2, d2 = twin.step(acts[0])
+    assert torch.equal(o1, o2) and torch.equal(r1, r2)
+    rollout_tuning(0)
+    assert env.rollout_plan(T, A, R, S)[0] > 0
+    env.rollout(acts, num_steps=T, out_obs=obs, out_rewards=rew, out_done=done, out_steps=steps)
+    for t in range(T):
+        o, r, d = twin.step(acts[t % A])
+    assert torch.equal(obs[(T - 1) % R], o) and torch.equal(rew[(T - 1) % S], r)
+    env.check()
+    twin.check()
+
+
+def test_rollout_persistent_full_size(rollout_tuning):
+    """BASELINE configs[1] size through the default path (persistent kernel, 3 environments per warp): 16 steps equal 16
+    whole-batch launches."""
+    import torch
+    B, N, L, T = 8192, 32, 40, 16
+    g = torch.Generator(device="cuda")
+    g.manual_seed(13)
+    acts = torch.randint(0, 5, (T, B, N), generator=g, device="cuda", dtype=torch.uint8)
+    ref = make_env(B, N, L)
+    ref.reset(seed=19, density=0.3)
+    env = make_env(B, N, L)
+    env.reset(seed=19, density=0.3)
+    assert env.rollout_plan(T, T, T, T)[0] == 0
+    obs, rew, done, steps = env.rollout(acts)
+    for t in range(T):
+        o, r, d = ref.step(acts[t])
+        assert torch.equal(obs[t], o), t
+        assert torch.equal(rew[t], r) and torch.equal(done[t], d)
+    assert torch.equal(env.agents_pos, ref.agents_pos)
+    assert int(steps[-1].min()) == T and int(steps[-1].max()) == T
+    env.check()
+
+
 def test_rollout_bad_arguments():
     import ctypes as C
     import torch
