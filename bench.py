@@ -312,10 +312,15 @@ def run_ours(args):
                        "extra_warmup": "0.3 s of untimed steps after W so SM clocks are under load"},
             "clocks": clocks,
             "gpu_launches": args.steps * chains if chains else 1,
-            "launch": {"api": "mapf_env_rollout (one call for the K steps)", "chains": chains, "envs_per_chain": per,
-                       "graph_period_steps": graph_period,
-                       "note": "each step of the batch = `chains` launches of step_observe_kernel over disjoint env ranges on "
-                               "internal streams; chains run out of phase, so one's stores overlap another's conflict resolution"},
+            "launch": ({"api": "mapf_env_rollout (one call for the K steps)", "chains": chains, "envs_per_chain": per,
+                        "graph_period_steps": graph_period,
+                        "note": "each step of the batch = `chains` launches of step_observe_kernel over disjoint env ranges on "
+                                "internal streams; chains run out of phase, so one's stores overlap another's conflict resolution"}
+                       if chains else
+                       {"api": "mapf_env_rollout (one call for the K steps)", "chains": 0, "kernel": "step_rollout_kernel (persistent)",
+                        "note": "ONE launch for the K steps: every resident warp takes its environments (4 each at this size) through "
+                                "all K steps, one environment after another; warps drift out of phase on their own and an "
+                                "environment's heuristic lines are re-read from L1 / L2"}),
             "single_launch": {"api": "mapf_env_step_observe, one whole-batch launch per step", "ms_per_step": ms_single / args.steps,
                               "value": world * B * N * args.steps / (ms_single * 1e-3),
                               "roofline_frac": algo_bytes(N, L) * B * N / (ms_single * 1e-3 / args.steps) / 1e9 / peak},
@@ -328,17 +333,22 @@ def run_ours(args):
                              "d2h_bytes_per_step": B * N * 4 + B * 5 + B * N * 486,
                              "api": "same call with the full observation tensor also copied to host (drop-in Environment.step)"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "kernel": "step_observe_kernel<RW=2,K=1,DO_STEP,4 warps,12 CTAs/SM>",
-                         "per_launch": {"algorithmic_bytes": algo_bytes(N, L) * per * N, "avg_duration_us": per_launch_s * 1e6,
-                                        "concurrent_launches": chains,
-                                        "note": "each chain's K launches run back to back for the whole timed region, so a launch "
-                                                "lasts one step period while sharing the GPU with the other chains' launches"},
-                         "achieved_is": "algorithmic bytes of one whole-batch step / step period in the timed region (the "
-                                        f"{chains} sub-batch launches of a step overlap those of its neighbours); `traffic` is "
-                                        "the ncu DRAM bytes of a whole-batch launch",
+                         "traffic": traffic, "kernel": ("step_rollout_kernel<RW=2,K=1,2 warps,64 regs> (persistent)" if not chains
+                                    else "step_observe_kernel<RW=2,K=1,DO_STEP,8 warps,64 regs>"),
+                         "per_launch": ({"algorithmic_bytes": algo_bytes(N, L) * per * N, "avg_duration_us": per_launch_s * 1e6,
+                                         "concurrent_launches": chains,
+                                         "note": "each chain's K launches run back to back for the whole timed region, so a launch "
+                                                 "lasts one step period while sharing the GPU with the other chains' launches"}
+                                        if chains else
+                                        {"algorithmic_bytes": algo_bytes(N, L) * B * N * args.steps, "avg_duration_us": ms * 1e3,
+                                         "concurrent_launches": 1, "note": "the one persistent launch covers all K steps"}),
+                         "achieved_is": "algorithmic bytes of one whole-batch step / step period in the timed region (steps of "
+                                        "different environments overlap inside the rollout); `traffic` is the ncu DRAM bytes of a "
+                                        "whole-batch single-step launch",
                          "algorithmic_bytes_per_agent_step": algo_bytes(N, L), "peak_source": peak_src,
-                         "note": "peak = measured copy (read+write) bandwidth; what plain write / mixed streams of this "
-                                 "shape reach on a B200 is in profiles/r1_membw_probe.jsonl"},
+                         "note": "peak = measured copy (read+write) bandwidth; the persistent rollout's traffic is almost write-only "
+                                 "(2 MB of DRAM reads per step, profiles/r1_rollout_persistent.log) and a pure write stream reaches "
+                                 "7.2 TB/s on a B200, so frac can exceed 1; plain write / mixed streams: profiles/r1_membw_probe.jsonl"},
         }
         if not args.no_cpu_baseline and world == 1:
             S = min(2048, B)

@@ -325,15 +325,15 @@ struct RolloutPlan {
 };
 // Process-wide knobs of the persistent rollout kernel (mapf_debug_rollout_tuning; read once from the environment):
 //   MAPF_ROLLOUT_PERSISTENT=0      never use it (chains of launches instead)
-//   MAPF_ROLLOUT_ENVS_PER_WARP=n   environments each resident warp takes through their T steps (0 = B / (24 warps per SM))
-//   MAPF_ROLLOUT_CTA_WARPS=1|2|4   warps per CTA
+//   MAPF_ROLLOUT_ENVS_PER_WARP=n   environments each resident warp takes through their T steps (0 = B / (16 warps per SM))
+//   MAPF_ROLLOUT_CTA_WARPS=1|2|4   warps per CTA (default 2)
 struct RolloutTuning {
     int persistent, envs_per_warp, cta_warps;
 };
 RolloutTuning &rollout_tuning()
 {
     static RolloutTuning t = [] {
-        RolloutTuning r{1, 0, 4};
+        RolloutTuning r{1, 0, 2};
         if (const char *s = std::getenv("MAPF_ROLLOUT_PERSISTENT")) r.persistent = std::atoi(s);
         if (const char *s = std::getenv("MAPF_ROLLOUT_ENVS_PER_WARP")) r.envs_per_warp = std::atoi(s);
         if (const char *s = std::getenv("MAPF_ROLLOUT_CTA_WARPS")) r.cta_warps = std::atoi(s);

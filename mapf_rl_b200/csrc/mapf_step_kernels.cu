@@ -122,16 +122,22 @@ template <int K>
 struct EnvRegs {
     int px[K], py[K];
     bool valid[K];
+    int gx[K], gy[K];  // goals and step counter: carried from step to step by the persistent rollout kernel only
+    int step;
 };
 
 // One warp, one environment: Environment.step (DO_STEP) and the observation BIT stream of all its agents.
 // On return the env's N*486-bit stream sits in s_bits starting at bit `head` (every lane has passed a
 // __syncwarp after its last write), positions / rewards / done / steps are stored, and the agent bitmap
 // still holds this env's bits (clear_agent_bits undoes them).
-template <int RW, int K, bool DO_STEP, bool TRACE = false, bool DO_OBS = true>
+// RESIDENT (persistent rollout kernel): when `carried` is set this is not the warp's first step of the env -- its obstacle
+// bitmap is still in s_obst and positions, goals and the step counter arrive in `out` from the previous call instead of
+// being loaded, so a step starts with one load (the action) instead of a round of them.
+template <int RW, int K, bool DO_STEP, bool TRACE = false, bool DO_OBS = true, bool RESIDENT = false>
 __device__ __forceinline__ void env_step_gather(const StepParams &p, const int e, const int lane, uint32_t *s_obst,
                                                 uint32_t *s_agent, uint32_t *s_bits, uint16_t *s_tgt, uint16_t *s_cell,
-                                                const int head, const uint64_t pol_keep, EnvRegs<K> &out)
+                                                const int head, const uint64_t pol_keep, EnvRegs<K> &out,
+                                                const bool carried = false)
 {
     constexpr int RWS = RW + 1;
     const EnvDims &d = p.d;
@@ -142,7 +148,7 @@ __device__ __forceinline__ void env_step_gather(const StepParams &p, const int e
     const bool navi_keep = p.flags & MAPF_STEPF_NAVI_KEEP;
     {
         // ---- request every input of this env up front ----
-        {
+        if (!(RESIDENT && carried)) {
             // obstacle bitmap: global -> shared without passing through registers (LDGSTS), so nothing below
             // waits for it until the cp.async.wait_all in front of the first __syncwarp
             const uint4 *src = reinterpret_cast<const uint4 *>(p.obst + (size_t)e * d.obst_stride);
@@ -160,7 +166,15 @@ __device__ __forceinline__ void env_step_gather(const StepParams &p, const int e
             valid[k] = a < N;
             px[k] = py[k] = 0;
             if constexpr (DO_STEP) gx[k] = gy[k] = act[k] = 0;
-            if (valid[k]) {
+            if (RESIDENT && carried) {
+                px[k] = out.px[k];
+                py[k] = out.py[k];
+                if constexpr (DO_STEP) {
+                    gx[k] = out.gx[k];
+                    gy[k] = out.gy[k];
+                    if (valid[k]) act[k] = __ldg(p.actions + (size_t)e * N + a);
+                }
+            } else if (valid[k]) {
                 const uchar2 pp = reinterpret_cast<const uchar2 *>(p.pos)[(size_t)e * N + a];
                 px[k] = pp.x;
                 py[k] = pp.y;
@@ -173,7 +187,7 @@ __device__ __forceinline__ void env_step_gather(const StepParams &p, const int e
             }
         }
         if constexpr (DO_STEP)
-            if (lane == 0) step_now = p.steps[e];
+            if (lane == 0) step_now = (RESIDENT && carried) ? out.step : p.steps[e];
         if constexpr (DO_STEP) {
             int tx[K], ty[K], tcell[K], mycell[K], occ_j[K];
             float rew[K];
@@ -399,7 +413,12 @@ __device__ __forceinline__ void env_step_gather(const StepParams &p, const int e
             out.px[k] = px[k];
             out.py[k] = py[k];
             out.valid[k] = valid[k];
+            if constexpr (RESIDENT && DO_STEP) {
+                out.gx[k] = gx[k];
+                out.gy[k] = gy[k];
+            }
         }
+        if constexpr (RESIDENT && DO_STEP) out.step = step_now + 1;
     }
 }
 
@@ -523,6 +542,7 @@ step_rollout_kernel(const StepParams p0, const RolloutArgs r)
     const size_t env_bytes = (size_t)N * MAPF_OBS_BYTES_PER_AGENT;
     for (int e = p0.env_begin + blockIdx.x * WARPS + warp; e < p0.env_end; e += gridDim.x * WARPS) {
         int sa = 0, so = 0, sr = 0;  // t % slots without a division per step
+        EnvRegs<K> regs;
         for (int t = 0; t < r.T; ++t) {
             StepParams p = p0;
             p.actions = r.actions + (size_t)sa * BN;
@@ -532,8 +552,8 @@ step_rollout_kernel(const StepParams p0, const RolloutArgs r)
             p.steps_out = r.steps_out ? r.steps_out + (size_t)sr * d.B : nullptr;
             uint8_t *obs_env = p.obs + (size_t)e * env_bytes;
             const int head = (int)(reinterpret_cast<uintptr_t>(obs_env) & 15);
-            EnvRegs<K> regs;
-            env_step_gather<RW, K, true>(p, e, lane, s_obst, s_agent, s_bits, s_tgt, s_cell, head, pol_keep, regs);
+            env_step_gather<RW, K, true, false, true, true>(p, e, lane, s_obst, s_agent, s_bits, s_tgt, s_cell, head, pol_keep, regs,
+                                                            t > 0);
             expand_store_block(p, obs_env, head, env_bytes, s_bits, lane, obs_policy, pol_stream);
             __syncwarp();
             clear_agent_bits<RW, K>(s_agent, regs);
@@ -976,18 +996,20 @@ int mapf_launch_rollout_persistent(mapf_env *env, int T, const uint8_t *d_action
     StepParams p = make_params(env);
     RolloutArgs r{T, action_slots, obs_slots, out_slots, d_actions, d_obs, d_rewards, d_done, d_steps};
     // Every warp of the (fully resident) grid takes the same number of environments through their T steps, one after another.
-    // Measured at 8192 x 32 agents (profiles/r1_rollout_persistent.log; us per step): 2 environments per warp 24.5, 3: 22.3,
-    // 4: 23.7, 6: 28.5, 8: 33.7 with 4-warp CTAs; 2-warp CTAs 22.6 / 22.3 at 3 / 4; 1-warp CTAs 25.9 / 28.0.  About 18 resident
-    // warps per SM: few enough for their environments' heuristic lines to stay in L1, enough to keep DRAM busy.
+    // Measured at 8192 x 32 agents (profiles/r1_rollout_persistent.log; us per step; state carried in registers):
+    //   2-warp CTAs: 2 environments per warp 23.0, 3: 21.7, 4: 21.3        4-warp CTAs: 2: 22.7, 3: 21.6, 4: 22.8
+    // (before the state was carried: 4-warp CTAs 24.5 / 22.3 / 23.7 / 24.1 / 28.5 / 33.7 at 2 / 3 / 4 / 5 / 6 / 8; 1-warp CTAs
+    // 25.9 / 28.0 at 3 / 4).  About 14-18 resident warps per SM: few enough for their environments' heuristic lines to stay in
+    // L1, enough to keep the DRAM write stream busy.
     int epw = envs_per_warp;
     if (epw <= 0) {
-        const int capacity = env->num_sms * 24;
+        const int capacity = env->num_sms * 16;
         epw = (env->d.B + capacity - 1) / capacity;
     }
     switch (cta_warps) {
         case 1: return launch_rollout_persistent_cfg<1>(env, p, r, epw, st);
-        case 2: return launch_rollout_persistent_cfg<2>(env, p, r, epw, st);
-        default: return launch_rollout_persistent_cfg<4>(env, p, r, epw, st);
+        case 4: return launch_rollout_persistent_cfg<4>(env, p, r, epw, st);
+        default: return launch_rollout_persistent_cfg<2>(env, p, r, epw, st);
     }
 }
 

@@ -191,7 +191,7 @@ def rollout_tuning():
     from mapf_rl_b200 import _native
     lib = _native.lib()
     yield lambda persistent=-1, envs_per_warp=-1, cta_warps=-1: lib.mapf_debug_rollout_tuning(persistent, envs_per_warp, cta_warps)
-    lib.mapf_debug_rollout_tuning(1, 0, 4)
+    lib.mapf_debug_rollout_tuning(1, 0, 2)
 
 
 @pytest.mark.parametrize("N,L,epw,cta_warps", [(20, 30, 0, 4), (20, 30, 3, 4), (32, 40, 5, 2), (7, 25, 2, 1), (32, 56, 4, 4)])
