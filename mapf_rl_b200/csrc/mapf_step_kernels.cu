@@ -50,6 +50,7 @@ enum : int {
     // diagnosis only (results are WRONG with these set; profiles/step_variants.py uses them to bound the kernel)
     MAPF_STEPF_DIAG_NO_NAVI = 4,   // skip the heuristic-map loads
     MAPF_STEPF_DIAG_NO_STORE = 8,  // skip the observation stores
+    MAPF_STEPF_DIAG_NO_STAGE = 128,  // step_only_kernel: every warp loads its own action row (no CTA-wide staging)
 };
 
 // 4 bits -> 4 bool bytes: bit b lands at bit 8b.  The four shifted copies of x (shifts 0,7,14,21)
@@ -137,7 +138,7 @@ template <int RW, int K, bool DO_STEP, bool TRACE = false, bool DO_OBS = true, b
 __device__ __forceinline__ void env_step_gather(const StepParams &p, const int e, const int lane, uint32_t *s_obst,
                                                 uint32_t *s_agent, uint32_t *s_bits, uint16_t *s_tgt, uint16_t *s_cell,
                                                 const int head, const uint64_t pol_keep, EnvRegs<K> &out,
-                                                const bool carried = false)
+                                                const bool carried = false, const uint8_t *s_act = nullptr)
 {
     constexpr int RWS = RW + 1;
     const EnvDims &d = p.d;
@@ -182,7 +183,7 @@ __device__ __forceinline__ void env_step_gather(const StepParams &p, const int e
                     const uchar2 gg = __ldg(reinterpret_cast<const uchar2 *>(p.goal) + (size_t)e * N + a);
                     gx[k] = gg.x;
                     gy[k] = gg.y;
-                    act[k] = __ldg(p.actions + (size_t)e * N + a);
+                    act[k] = s_act ? s_act[a] : __ldg(p.actions + (size_t)e * N + a);
                 }
             }
         }
@@ -580,9 +581,23 @@ step_only_kernel(const StepParams p)
     uint16_t *s_tgt = reinterpret_cast<uint16_t *>(s_bits + p.bits_words);
     uint16_t *s_cell = s_tgt + 32 * K;
     const int e = blockIdx.x * 4 + warp;
+    // The CTA's four action rows are contiguous (4 N bytes): fetched as 16-byte words, they are a few 128-byte requests per
+    // CTA instead of one 32-byte request per warp -- mapf_env_step_host points `actions` at page-locked HOST memory and the
+    // kernel's time is the PCIe round trips of this load.
+    __shared__ __align__(16) uint8_t s_actions[4 * MAPF_MAX_AGENTS];
+    const int N = p.d.N;
+    const uint8_t *rows = p.actions + (size_t)blockIdx.x * 4 * N;
+    const int nbytes = min(4, p.d.B - (int)blockIdx.x * 4) * N;
+    const bool staged = ((reinterpret_cast<uintptr_t>(rows) | (uintptr_t)nbytes) & 15) == 0 && !(p.flags & MAPF_STEPF_DIAG_NO_STAGE);
+    if (staged) {
+        for (int w = threadIdx.x; w < (nbytes >> 4); w += blockDim.x)
+            reinterpret_cast<uint4 *>(s_actions)[w] = __ldg(reinterpret_cast<const uint4 *>(rows) + w);
+    }
+    __syncthreads();
     if (e >= p.d.B) return;
     EnvRegs<K> r;
-    env_step_gather<RW, K, true, false, false>(p, e, lane, s_obst, s_agent, s_bits, s_tgt, s_cell, 0, 0ull, r);
+    env_step_gather<RW, K, true, false, false>(p, e, lane, s_obst, s_agent, s_bits, s_tgt, s_cell, 0, 0ull, r, false,
+                                               staged ? s_actions + warp * N : nullptr);
 }
 
 // ---- K1+K2, split form (the hot path) -----------------------------------------------------------------
