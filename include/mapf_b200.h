@@ -120,12 +120,12 @@ int mapf_env_observe_rows(mapf_env *env, uint8_t *d_obs_base, const int64_t *d_o
  * With chains = 0 on the hot geometry (maps of 25..56 cells, up to 32 agents, B >= 2048, T >= 16) the rollout is ONE launch of
  * a persistent kernel: every resident warp takes its environments through all T steps, one environment after another, so
  * nothing is launched between steps, the warps drift out of phase on their own and an environment's heuristic lines are re-read
- * from L1 / L2 (22.3 us per step at 8192 x 32 agents).  Otherwise the batch runs as `chains`
+ * from L1 / L2 (21.3 us per step at 8192 x 32 agents).  Otherwise the batch runs as `chains`
  * contiguous sub-batches (1..MAPF_MAX_CHAINS; 0 = default: 1 below 2048 environments, else 4, or 8 when the rollout is long
  * enough to be replayed from graphs), each an independent chain of T launches on a stream of its own: launch t+1 of a chain
  * waits for launch t of THAT chain only, the chains drift out of phase, and the observation stores of one overlap the
- * conflict resolution of another (one launch over the whole batch keeps every warp in the same phase: 34 us per step at
- * 8192 x 32 agents, 25.7 us as 8 chains; profiles/).  When T covers at least 4 periods P = lcm(slot counts) <= 64, whole
+ * conflict resolution of another (one launch over the whole batch keeps every warp in the same phase: 33 us per step at
+ * 8192 x 32 agents, 24.1 us as 8 chains; profiles/).  When T covers at least 4 periods P = lcm(slot counts) <= 64, whole
  * periods are replayed from per-chain CUDA graphs captured once per argument set (the host cost of a launch, ~4 us, would
  * otherwise bound 8 chains at 32 us per step).
  * The call forks from `stream` and joins back into it; it returns when everything is queued (asynchronous). */
