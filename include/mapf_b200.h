@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define MAPF_ABI_VERSION 1
+#define MAPF_ABI_VERSION 2
 
 #define MAPF_OK 0
 #define MAPF_EINVAL (-1)   /* bad argument (shape, NULL, unsupported size)          */
@@ -42,6 +42,22 @@ extern "C" {
 #define MAPF_EUNIQUE (-4)  /* two agents share a cell (environment.py:424-428)       */
 #define MAPF_ENOMEM (-5)
 #define MAPF_ENOSPACE (-6) /* reset could not place the agents ('no empty position', environment.py:31) */
+#define MAPF_ESTATE (-7)   /* load / set_state: coordinate outside the map or slot id outside the batch (the reference raises
+                              IndexError on the same input; two agents on one cell latch MAPF_EUNIQUE) */
+#define MAPF_EINTERNAL (-8) /* the rollout scheduler gave up waiting for a chunk hand-over (a bug, never expected) */
+#define MAPF_EINDEX (-9)   /* sum tree: a leaf index outside [0, capacity) was skipped (numpy raises IndexError) */
+
+/* Reward codes: the position of an agent's reward in reward_fn (config.py:8-12).  Every step entry point can emit these
+ * u8 codes instead of / next to the fp32 rewards: a reward takes one of five values, so the host side of an actor reads
+ * B*N bytes per step instead of 4*B*N and looks the value up in its 5-entry table. */
+#define MAPF_RCODE_MOVE 0
+#define MAPF_RCODE_STAY_ON_GOAL 1
+#define MAPF_RCODE_STAY_OFF_GOAL 2
+#define MAPF_RCODE_COLLISION 3
+#define MAPF_RCODE_FINISH 4
+#define MAPF_RCODE_RESET 5 /* reward 0: the step re-generated the environment (mapf_env_set_autoreset) */
+#define MAPF_RCODE_STAY_ON MAPF_RCODE_STAY_ON_GOAL
+#define MAPF_RCODE_STAY_OFF MAPF_RCODE_STAY_OFF_GOAL
 
 #define MAPF_OBS_RADIUS 4  /* config.py:14 — the only radius any reference consumer uses */
 #define MAPF_FOV 9
@@ -100,6 +116,11 @@ int mapf_env_bfs_navi(mapf_env *env, const int32_t *d_env_ids, int32_t n, int32_
 int mapf_env_step_observe(mapf_env *env, const uint8_t *d_actions, uint8_t *d_obs, float *d_rewards,
                           uint8_t *d_done, int32_t *d_steps, void *stream);
 
+/* The same step with every output optional but d_done: d_rewards f32[B, N] and / or d_codes u8[B, N] (MAPF_RCODE_*),
+ * d_obs_rows (optional) as in mapf_env_step_observe_rows. */
+int mapf_env_step_observe_ex(mapf_env *env, const uint8_t *d_actions, uint8_t *d_obs, const int64_t *d_obs_rows,
+                             float *d_rewards, uint8_t *d_codes, uint8_t *d_done, int32_t *d_steps, void *stream);
+
 /* Environment.observe (environment.py:433-467).  d_pos (optional) u8[B, N, 2]. */
 int mapf_env_observe(mapf_env *env, uint8_t *d_obs, uint8_t *d_pos, void *stream);
 
@@ -116,23 +137,53 @@ int mapf_env_observe_rows(mapf_env *env, uint8_t *d_obs_base, const int64_t *d_o
  * t % obs_slots and rewards / done / steps slot t % out_slots; results equal T calls of mapf_env_step_observe.
  *   d_actions u8[action_slots, B, N]   d_obs u8[obs_slots, B, N, 6, 9, 9]
  *   d_rewards f32[out_slots, B, N]     d_done u8[out_slots, B]     d_steps i32[out_slots, B] (optional)
- * Environments are independent (no reference code path couples two Environment objects), so the batch runs as `chains`
- * With chains = 0 on the hot geometry (maps of 25..56 cells, up to 32 agents, B >= 2048, T >= 16) the rollout is ONE launch of
- * a persistent kernel: every resident warp takes its environments through all T steps, one environment after another, so
- * nothing is launched between steps, the warps drift out of phase on their own and an environment's heuristic lines are re-read
- * from L1 / L2 (21.3 us per step at 8192 x 32 agents).  Otherwise the batch runs as `chains`
- * contiguous sub-batches (1..MAPF_MAX_CHAINS; 0 = default: 1 below 2048 environments, else 4, or 8 when the rollout is long
- * enough to be replayed from graphs), each an independent chain of T launches on a stream of its own: launch t+1 of a chain
- * waits for launch t of THAT chain only, the chains drift out of phase, and the observation stores of one overlap the
- * conflict resolution of another (one launch over the whole batch keeps every warp in the same phase: 33 us per step at
- * 8192 x 32 agents, 24.1 us as 8 chains; profiles/).  When T covers at least 4 periods P = lcm(slot counts) <= 64, whole
- * periods are replayed from per-chain CUDA graphs captured once per argument set (the host cost of a launch, ~4 us, would
- * otherwise bound 8 chains at 32 us per step).
- * The call forks from `stream` and joins back into it; it returns when everything is queued (asynchronous). */
+ * Environments are independent (no reference code path couples two Environment objects).  With chains = 0 and up to 64
+ * agents the rollout is ONE launch of a persistent kernel (mapf_rollout_kernels.cu): the rollout is cut into work items
+ * (environment, chunk of consecutive steps) that resident warps claim time-major from a global counter; a warp keeps the
+ * environment's state in registers / shared memory for the steps of its item, each agent's current 16x16 heuristic tile is
+ * cached in shared memory, warps drift out of phase on their own (one's observation stores overlap another's conflict
+ * resolution) and nothing is launched between steps.  With chains >= 1 (or more than 64 agents) the batch runs as `chains`
+ * contiguous sub-batches (1..MAPF_MAX_CHAINS), each an independent chain of T single-step launches on a stream of its own;
+ * when T covers at least 4 periods P = lcm(slot counts) <= 64, whole periods are replayed from per-chain CUDA graphs.
+ * The call forks from `stream` and joins back into it; it returns when everything is queued (asynchronous).
+ * One handle runs one rollout at a time. */
 #define MAPF_MAX_CHAINS 16
 int mapf_env_rollout(mapf_env *env, int32_t T, const uint8_t *d_actions, int32_t action_slots, uint8_t *d_obs,
                      int32_t obs_slots, float *d_rewards, uint8_t *d_done, int32_t *d_steps, int32_t out_slots,
                      int32_t chains, void *stream);
+
+/* mapf_env_rollout with every output ring optional but d_done, plus reward codes. */
+typedef struct mapf_rollout_io {
+    int32_t T;               /* steps                                                            */
+    const uint8_t *d_actions; /* u8[action_slots, B, N]                                           */
+    int32_t action_slots;
+    uint8_t *d_obs;          /* u8[obs_slots, B, N, 6, 9, 9]                                     */
+    int32_t obs_slots;
+    float *d_rewards;        /* f32[out_slots, B, N] or NULL                                     */
+    uint8_t *d_codes;        /* u8[out_slots, B, N] or NULL (MAPF_RCODE_*)                       */
+    uint8_t *d_done;         /* u8[out_slots, B]                                                 */
+    int32_t *d_steps;        /* i32[out_slots, B] or NULL                                        */
+    int32_t out_slots;
+    int32_t chains;          /* 0 = persistent kernel where it is served, else chains            */
+} mapf_rollout_io;
+int mapf_env_rollout_ex(mapf_env *env, const mapf_rollout_io *io, void *stream);
+
+/* Episode handling inside mapf_env_rollout (the actor loop's `if done or env.steps >= max_steps: reset()`,
+ * worker.py:390,422-428, config.py:29).  With max_steps > 0, a rollout step that finds its environment finished (all agents
+ * on their goals after the previous step, or steps >= max_steps) does not move anybody: it draws a NEW instance for the
+ * slot on the device (generator + heuristic maps, exactly what mapf_env_reset(mask = {e}, seed, env_offset + n * stride,
+ * density) draws for the slot's n-th re-generation, n = 1, 2, ...), emits that instance's first observation, rewards 0
+ * (MAPF_RCODE_RESET), done 0 and steps 0, and ignores the step's actions.  The step before it carries the terminal
+ * observation / rewards / done / steps exactly as without episode handling.  `stride` = number of environments of the
+ * whole job (all GPUs), so re-generated instances never collide with another slot's.  max_steps = 0 switches it off.
+ * Only the persistent kernel serves it (up to 64 agents).  The call also zeroes the per-slot episode counters. */
+int mapf_env_set_autoreset(mapf_env *env, int32_t max_steps, uint64_t seed, uint64_t env_offset, uint64_t stride,
+                           float density, void *stream);
+
+/* check_unique != 0: every step verifies that no two agents share a cell afterwards (environment.py:424-428) and latches
+ * MAPF_EUNIQUE otherwise (read by mapf_env_status).  Off by default: a correct step from a valid state cannot violate it,
+ * and load / set_state validate what they are given. */
+int mapf_env_set_checks(mapf_env *env, int32_t check_unique);
 
 /* How mapf_env_rollout would run these arguments: number of chains, environments per chain, and the number of steps per
  * replayed graph (0 = every step launched directly).  chains_out = 0 means the persistent kernel: one launch for the whole
@@ -140,39 +191,40 @@ int mapf_env_rollout(mapf_env *env, int32_t T, const uint8_t *d_actions, int32_t
 int mapf_env_rollout_plan(mapf_env *env, int32_t T, int32_t action_slots, int32_t obs_slots, int32_t out_slots,
                           int32_t chains, int32_t *chains_out, int32_t *envs_per_chain_out, int32_t *graph_period_out);
 
-/* Host-buffer variant of step (what a per-process actor calls): copies actions H2D, runs the fused
- * kernel, copies rewards / done / steps (and obs if h_obs != NULL) D2H, then synchronises.
- * All h_* buffers are ordinary or page-locked host memory; page-locked ones (cudaHostAlloc /
- * cudaHostRegister / torch pin_memory) are used as DMA endpoints directly, pageable ones are staged through
- * the handle's own pinned area.  By default the call runs the step kernel (which reads page-locked actions in
- * place over PCIe), then the observe kernel WHILE rewards / done / steps are copied to the host on a side stream,
- * the whole sequence captured once per buffer set into a CUDA graph and replayed with one launch; MAPF_STEP_HOST_MODE
- * in the environment selects the simpler forms (0 = copies around the fused kernel ... 4 = default, see mapf_abi.cu).
- * What a host pointer resolves to is cached per handle: keep a buffer registered for as long as it is passed.
- * d_obs_opt: if non-NULL the observation is written there (device replay
- * tensor) instead of an internal buffer. */
+/* Host-buffer variant of step (what a per-process actor calls): actions in host memory in, rewards / done / steps (and
+ * obs if h_obs != NULL) in host memory out, synchronous.  All h_* buffers are ordinary or page-locked host memory;
+ * page-locked ones (cudaHostAlloc / cudaHostRegister / torch pin_memory) are used in place, pageable ones are staged
+ * through the handle's own pinned area.  The call runs the step kernel (which reads page-locked actions in place over
+ * PCIe), then the observe kernel WHILE rewards / done / steps are copied to the host on a side stream, captured once per
+ * buffer set into a CUDA graph.  What a host pointer resolves to is re-validated on every call (a freed and re-used
+ * address is detected).  d_obs_opt: if non-NULL the observation is written there (device replay tensor) instead of an
+ * internal buffer. */
 int mapf_env_step_host(mapf_env *env, const uint8_t *h_actions, uint8_t *h_obs, float *h_rewards,
                        uint8_t *h_done, int32_t *h_steps, uint8_t *d_obs_opt, void *stream);
 
-/* Diagnostics / tuning (process-wide; profiles/step_variants.py, tests): selects the step kernel form.
- *   variant     >= 10: split producer/consumer kernel (10 = default shape, 11..17 other warp splits);
- *               0..9: single-role kernel; 1 (default) picks the CTA shape per launch, the others force one (see
- *               launch_step_rwk in mapf_step_kernels.cu);  < 0 leaves the current value
- *   flags       MAPF_STEPF_* bit set of mapf_step_kernels.cu (1 = L2 evict_last on heuristic-map loads); < 0 keeps
+/* The throughput form of the host-buffer step: reward CODES (u8[B, N], MAPF_RCODE_*) instead of fp32 rewards, ONE fused
+ * kernel, no DMA nodes.  The kernel reads the page-locked actions in place, and every environment stores its codes / done /
+ * steps straight into the (page-locked) host buffers as soon as its conflict resolution is done; the last one raises a
+ * host flag.  The call returns when the flag is up: h_codes / h_done / h_steps are final, while the observation stores
+ * into d_obs (required, device memory) are still draining on `stream` -- they are ordered before anything queued on
+ * `stream` afterwards, including the next step.  Pageable host buffers are staged as above. */
+int mapf_env_step_host_codes(mapf_env *env, const uint8_t *h_actions, uint8_t *h_codes, uint8_t *h_done, int32_t *h_steps,
+                             uint8_t *d_obs, void *stream);
+
+/* Tuning (process-wide; profiles/, tests): CTA shape of the single-launch step kernel.
+ *   variant     1 (default) picks the CTA shape per launch, 0 / 7 / 8 / 4 / 9 force one (launch_step_rwk in
+ *               mapf_step_kernels.cu);  < 0 leaves the current value
+ *   flags       1 = L2 evict_last on heuristic-map loads, 2 = L2 evict_first policy on observation stores; < 0 keeps
  *   ctas_per_sm cap on resident CTAs per SM (0 = as many as fit); < 0 keeps
  * The same three values are read once from MAPF_STEP_VARIANT / MAPF_STEP_FLAGS / MAPF_STEP_CTAS_PER_SM. */
 int mapf_debug_step_tuning(int32_t variant, int32_t flags, int32_t ctas_per_sm);
 /* Knobs of the persistent kernel behind mapf_env_rollout (process-wide; < 0 keeps a value): persistent 0 = never use it,
- * envs_per_warp = environments each resident warp takes through their T steps (0 = automatic), cta_warps = 1, 2 or 4.
- * Read once from MAPF_ROLLOUT_PERSISTENT / MAPF_ROLLOUT_ENVS_PER_WARP / MAPF_ROLLOUT_CTA_WARPS. */
-int mapf_debug_rollout_tuning(int32_t persistent, int32_t envs_per_warp, int32_t cta_warps);
-/* Selects the form of mapf_env_step_host (0..4, see there; < 0 only queries); returns the mode in force. */
+ * warps_per_sm = resident warps per SM (0 = 16), chunk = steps per work item (0 = automatic), store_mode 0 = direct
+ * 16-byte stores / 1 = bulk (TMA) stores from a shared-memory staging block, stagger_ns = spread of the warps' start.
+ * Read once from MAPF_ROLLOUT_PERSISTENT / _WARPS_PER_SM / _CHUNK / _STORE_MODE / _STAGGER_NS. */
+int mapf_debug_rollout_tuning(int32_t persistent, int32_t warps_per_sm, int32_t chunk, int32_t store_mode, int32_t stagger_ns);
+/* Selects the form of mapf_env_step_host (0..4, see mapf_abi.cu; < 0 only queries); returns the mode in force. */
 int mapf_debug_step_host_mode(int32_t mode);
-/* Diagnosis: while d_trace != NULL (u64[B, 16], device) the split step kernel stamps %globaltimer per environment:
- * [0] producer reaches the env, [1] its slot is free, [7] inputs loaded, [8] conflicts resolved, [2] step phase
- * done (state stored), [9] before / [10] after the window gather of agent 0, [3] bit stream published,
- * [4] consumer reaches the env, [5] stream available, [6] stores issued.  NULL switches it off. */
-int mapf_debug_step_trace(uint64_t *d_trace);
 
 /* ---- communication mask of Network.step (model.py:196-208), the actor-side glue next to observe() ------
  *   d_mask_out u8[B, N, N]: mask[i][j] = 1 iff agent j is inside agent i's 9x9 field of view (|dx| <= 4 and
@@ -189,7 +241,8 @@ int mapf_env_get_state(mapf_env *env, uint8_t *d_map, uint8_t *d_pos, uint8_t *d
 /* Overwrite agent positions / step counters (used to restore snapshots). Either may be NULL. */
 int mapf_env_set_state(mapf_env *env, const uint8_t *d_pos, const int32_t *d_steps, void *stream);
 
-/* Synchronous: returns the latched error (MAPF_OK, MAPF_EACTION, MAPF_EUNIQUE, MAPF_ENOSPACE) and clears it. */
+/* Synchronous: returns the latched error (MAPF_OK, MAPF_EACTION, MAPF_EUNIQUE, MAPF_ENOSPACE, MAPF_ESTATE,
+ * MAPF_EINTERNAL) and clears it. */
 int mapf_env_status(mapf_env *env, void *stream);
 
 /* ---- Environment.reset instance generation (environment.py:146-196), device side ----------- */
@@ -235,6 +288,34 @@ int mapf_per_td_update(mapf_per *tree, const float *d_q_online, const float *d_q
                        double alpha, int64_t old_ptr, int64_t ptr, int64_t slot_steps, float *d_td_out,
                        float *d_prio_out, void *stream);
 
+/* One learner cycle in ONE launch (north star (4)): the priorities of the batch that has just been through the two Q
+ * forwards go into the tree (the mapf_per_td_update half), then the NEXT batch is drawn from the refreshed tree with its
+ * importance-sampling weights (the mapf_per_sample half).  Either half may be empty (n_update / n_sample = 0). */
+typedef struct mapf_per_cycle_args {
+    /* update half: arguments of mapf_per_td_update */
+    const float *d_q_online, *d_q_target_next, *d_q_online_next;
+    const int64_t *d_action;
+    const float *d_reward, *d_done, *d_steps;
+    const int64_t *d_idx;
+    int64_t n_update;
+    float gamma;
+    double alpha;
+    int64_t old_ptr, ptr, slot_steps;
+    float *d_td_out, *d_prio_out;
+    /* sample half: arguments of mapf_per_sample */
+    const double *d_uniforms;
+    int64_t n_sample;
+    int64_t *d_sample_idx_out;
+    double *d_sample_prio_out;
+    float *d_sample_weight_out;
+    double beta;
+} mapf_per_cycle_args;
+int mapf_per_cycle(mapf_per *tree, const mapf_per_cycle_args *args, void *stream);
+
+/* Synchronous: MAPF_EINDEX if an update since the last call was handed a leaf index outside [0, capacity) (such entries
+ * are skipped), else MAPF_OK; clears the latch.  One tree handle is used from one stream at a time. */
+int mapf_per_status(mapf_per *tree, void *stream);
+
 /* LocalBuffer.finish TD (buffer.py:170-177) for `episodes` episodes of up to `capacity` steps:
  *   td[e,t] = | r[e,t] + 0.99*r[e,t+1] + max_a q[e,t,a] - q[e,t,act[e,t]] |,  0 for t >= size[e]
  *   d_rew f32[episodes, capacity] (already rounded through fp16 by the caller, buffer.py:122),
@@ -242,6 +323,10 @@ int mapf_per_td_update(mapf_per *tree, const float *d_q_online, const float *d_q
  *   d_td_out f64[episodes, capacity]. */
 int mapf_actor_td(const float *d_rew, const float *d_q, const uint8_t *d_act, const int32_t *d_size,
                   int32_t episodes, int32_t capacity, double *d_td_out, void *stream);
+/* The same for config.forward_steps = n (1..8) and another discount: td = | sum_{j<n} gamma^j r[e,t+j] + max_a q - q[a_t] |
+ * (buffer.py:174-175 builds the kernel [0.99^(n-1), ..., 1] from config.forward_steps; mapf_actor_td is n = 2, 0.99). */
+int mapf_actor_td_n(const float *d_rew, const float *d_q, const uint8_t *d_act, const int32_t *d_size, int32_t episodes,
+                    int32_t capacity, int32_t forward_steps, double gamma, double *d_td_out, void *stream);
 
 /* ---- GlobalBuffer.sample_batch window gather (worker.py:106-184) -------------------------------- */
 /* Device-resident replay store in the reference's logical layout (worker.py:36-42): episode slot g owns

@@ -170,7 +170,8 @@ class BatchedActor:
         leaves = (slots[:, None] * S + torch.arange(S, device=self.dev)[None, :])
         rew = st.rew_buf[leaves].float()
         act = st.act_buf[leaves]
-        td = actor_td_errors(rew, self.q_buf[idt], act, size.to(torch.int32), capacity=S, device=self.dev)
+        td = actor_td_errors(rew, self.q_buf[idt], act, size.to(torch.int32), capacity=S, device=self.dev,
+                             forward_steps=st.forward_steps)
         st.priority_tree.update_device(leaves.reshape(-1), td.reshape(-1) ** st.alpha)
         st.done_buf[slots] = done.to(torch.uint8)
         st.size_buf[slots] = size.to(torch.int32)

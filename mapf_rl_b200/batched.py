@@ -45,6 +45,7 @@ class BatchedEnvironment:
         self._rewards = torch.empty((B, N), dtype=torch.float32, device=self.device)
         self._done = torch.empty((B,), dtype=torch.uint8, device=self.device)
         self._steps = torch.empty((B,), dtype=torch.int32, device=self.device)
+        self._resets = 0
 
     # -- plumbing ------------------------------------------------------------------------------
     def close(self):
@@ -71,6 +72,18 @@ class BatchedEnvironment:
         assert tuple(t.shape) == tuple(shape), f"expected shape {shape}, got {tuple(t.shape)}"
         return t
 
+    def _coords_u8(self, x, shape):
+        """Coordinates -> uint8 tensor on this device; anything outside [0, L) raises here instead of wrapping in the
+        uint8 cast (the reference raises IndexError when it indexes the map with such a coordinate)."""
+        torch = _torch()
+        t = x if isinstance(x, torch.Tensor) else torch.as_tensor(np.ascontiguousarray(x))
+        assert tuple(t.shape) == tuple(shape), f"expected shape {shape}, got {tuple(t.shape)}"
+        if t.dtype != torch.uint8 or self.map_length < 256:
+            lo, hi = (int(t.min()), int(t.max())) if t.numel() else (0, 0)
+            if lo < 0 or hi >= self.map_length:
+                raise IndexError(f"coordinate outside the {self.map_length}x{self.map_length} map: min {lo}, max {hi}")
+        return t.to(device=self.device, dtype=torch.uint8).contiguous()
+
     @property
     def arena_bytes(self) -> int:
         return int(self._lib.mapf_env_arena_bytes(self._h))
@@ -83,8 +96,8 @@ class BatchedEnvironment:
         L, N = self.map_length, self.num_agents
         n = int(maps.shape[0])
         m = self._dev_u8(maps, (n, L, L), as_mask=True)
-        a = self._dev_u8(agents_pos, (n, N, 2))
-        g = self._dev_u8(goals_pos, (n, N, 2))
+        a = self._coords_u8(agents_pos, (n, N, 2))
+        g = self._coords_u8(goals_pos, (n, N, 2))
         ids_ptr = None
         if env_ids is not None:
             ids = torch.as_tensor(env_ids, dtype=torch.int32).to(self.device).contiguous()
@@ -92,12 +105,20 @@ class BatchedEnvironment:
             ids_ptr = C.c_void_p(ids.data_ptr())
         _native.check(self._lib.mapf_env_load(self._h, ids_ptr, n, C.c_void_p(m.data_ptr()), C.c_void_p(a.data_ptr()),
                                               C.c_void_p(g.data_ptr()), self._stream()))
-        # keep inputs alive until the stream has consumed them
-        torch.cuda.current_stream(self.device).synchronize()
+        # synchronous (keeps the inputs alive until the stream has consumed them); raises IndexError if the device-side
+        # validation found a coordinate outside the map / a slot id outside the batch, RuntimeError('unique') for two
+        # agents on one cell (environment.py:424-428 raises that at the next step)
+        self.check()
 
     # -- Environment.reset generator, device side (environment.py:146-196) ----------------------
-    def reset(self, mask=None, seed: int = 0, env_offset: int = 0, density: Optional[float] = None):
-        """Draw new random instances on the device for slots with mask != 0 (default: all)."""
+    def reset(self, mask=None, seed: int = 0, env_offset: Optional[int] = None, density: Optional[float] = None):
+        """Draw new random instances on the device for slots with mask != 0 (default: all).  Slot e draws Philox stream
+        (seed, env_offset + e).  Without an explicit `env_offset` the handle counts its resets and uses
+        resets * num_envs, so repeated `reset(mask)` calls at episode ends never hand a slot the instance it (or another
+        slot) had before; pass `env_offset` to pin the instances (sharding, reproducing a run)."""
+        if env_offset is None:
+            env_offset = self._resets * self.num_envs
+        self._resets += 1
         mptr = None
         if mask is not None:
             mk = self._dev_u8(mask, (self.num_envs,))
@@ -107,12 +128,13 @@ class BatchedEnvironment:
                                                C.c_float(dens), self._stream()))
 
     # -- Environment.step + observe (environment.py:278-467) -------------------------------------
-    def step(self, actions, out_obs=None, out_rewards=None, out_done=None, obs_rows=None):
+    def step(self, actions, out_obs=None, out_rewards=None, out_done=None, obs_rows=None, out_codes=None):
         """actions: uint8 CUDA tensor [B,N] (anything else is converted).
         Returns (obs uint8[B,N,6,9,9], rewards float32[B,N], done uint8[B]); obs is written into
         `out_obs` when given (e.g. a slot of a device replay tensor).  With `obs_rows` (int64 CUDA tensor [B]),
         `out_obs` is the whole observation buffer of a replay store ([rows,N,6,9,9]) and environment e writes
-        its block at row obs_rows[e] (returned obs is then `out_obs` itself)."""
+        its block at row obs_rows[e] (returned obs is then `out_obs` itself).  `out_codes` (uint8 CUDA tensor [B,N])
+        additionally receives the reward codes (index into config.REWARD_ORDER)."""
         torch = _torch()
         B, N = self.num_envs, self.num_agents
         if not (isinstance(actions, torch.Tensor) and actions.dtype == torch.uint8 and actions.is_cuda
@@ -123,28 +145,32 @@ class BatchedEnvironment:
         obs = out_obs if out_obs is not None else torch.empty((B, N, *self.OBS_SHAPE), dtype=torch.uint8, device=self.device)
         rewards = out_rewards if out_rewards is not None else self._rewards
         done = out_done if out_done is not None else self._done
+        rows_ptr = None
         if obs_rows is not None:
             assert out_obs is not None and obs.is_contiguous() and obs.dtype == torch.uint8 and obs.shape[1] == N
             assert obs_rows.dtype == torch.int64 and obs_rows.is_cuda and obs_rows.numel() == B
-            _native.check(self._lib.mapf_env_step_observe_rows(
-                self._h, C.c_void_p(actions.data_ptr()), C.c_void_p(obs.data_ptr()), C.c_void_p(obs_rows.data_ptr()),
-                C.c_void_p(rewards.data_ptr()), C.c_void_p(done.data_ptr()), C.c_void_p(self._steps.data_ptr()), self._stream()))
-            return obs, rewards, done
-        assert obs.is_contiguous() and obs.dtype == torch.uint8 and obs.numel() == B * N * 486
-        _native.check(self._lib.mapf_env_step_observe(self._h, C.c_void_p(actions.data_ptr()), C.c_void_p(obs.data_ptr()),
-                                                      C.c_void_p(rewards.data_ptr()), C.c_void_p(done.data_ptr()),
-                                                      C.c_void_p(self._steps.data_ptr()), self._stream()))
+            rows_ptr = C.c_void_p(obs_rows.data_ptr())
+        else:
+            assert obs.is_contiguous() and obs.dtype == torch.uint8 and obs.numel() == B * N * 486
+        codes_ptr = None
+        if out_codes is not None:
+            assert out_codes.is_cuda and out_codes.dtype == torch.uint8 and out_codes.is_contiguous() and out_codes.numel() == B * N
+            codes_ptr = C.c_void_p(out_codes.data_ptr())
+        _native.check(self._lib.mapf_env_step_observe_ex(
+            self._h, C.c_void_p(actions.data_ptr()), C.c_void_p(obs.data_ptr()), rows_ptr, C.c_void_p(rewards.data_ptr()),
+            codes_ptr, C.c_void_p(done.data_ptr()), C.c_void_p(self._steps.data_ptr()), self._stream()))
         return obs, rewards, done
 
     def rollout(self, actions, num_steps: Optional[int] = None, out_obs=None, out_rewards=None, out_done=None,
-                out_steps=None, chains: int = 0):
+                out_steps=None, chains: int = 0, out_codes=None):
         """`num_steps` lockstep steps with the actions already on the device (mapf_env_rollout): the loop
         `for t: env.step(actions[t])` of test.py:120-130 when the actions do not depend on the observations.
         actions uint8[A,B,N] (step t uses slot t % A; num_steps defaults to A); out_obs uint8[R,B,N,6,9,9],
         out_rewards float32[S,B,N], out_done uint8[S,B], out_steps int32[S,B] are rings indexed t % R / t % S
         (allocated with one slot per step when not given).  The batch runs as `chains` independent sub-batch chains
-        on internal streams (0 = default).  Asynchronous on the current stream.
-        Returns (obs, rewards, done, steps) rings."""
+        on internal streams (0 = default: one launch of the persistent rollout kernel).  `out_codes` uint8[S,B,N]
+        additionally receives reward codes; `out_rewards=False` skips the fp32 rewards (codes only).  Asynchronous on
+        the current stream.  Returns (obs, rewards, done, steps) rings."""
         torch = _torch()
         B, N = self.num_envs, self.num_agents
         assert isinstance(actions, torch.Tensor) and actions.is_cuda and actions.dtype == torch.uint8 and actions.is_contiguous()
@@ -152,19 +178,44 @@ class BatchedEnvironment:
         A = int(actions.shape[0])
         T = A if num_steps is None else int(num_steps)
         obs = out_obs if out_obs is not None else torch.empty((T, B, N, *self.OBS_SHAPE), dtype=torch.uint8, device=self.device)
-        rewards = out_rewards if out_rewards is not None else torch.empty((T, B, N), dtype=torch.float32, device=self.device)
-        S = int(rewards.shape[0])
+        if out_rewards is False:
+            assert out_codes is not None, "out_rewards=False needs out_codes"
+            rewards = None
+            S = int(out_codes.shape[0])
+        else:
+            rewards = out_rewards if out_rewards is not None else torch.empty((T, B, N), dtype=torch.float32, device=self.device)
+            S = int(rewards.shape[0])
         done = out_done if out_done is not None else torch.empty((S, B), dtype=torch.uint8, device=self.device)
         steps = out_steps if out_steps is not None else torch.empty((S, B), dtype=torch.int32, device=self.device)
         assert obs.is_contiguous() and obs.dtype == torch.uint8 and tuple(obs.shape[1:]) == (B, N, *self.OBS_SHAPE)
-        assert rewards.is_contiguous() and rewards.dtype == torch.float32 and tuple(rewards.shape) == (S, B, N)
+        assert rewards is None or (rewards.is_contiguous() and rewards.dtype == torch.float32 and tuple(rewards.shape) == (S, B, N))
         assert done.is_contiguous() and done.dtype == torch.uint8 and tuple(done.shape) == (S, B)
         assert steps.is_contiguous() and steps.dtype == torch.int32 and tuple(steps.shape) == (S, B)
-        _native.check(self._lib.mapf_env_rollout(
-            self._h, T, C.c_void_p(actions.data_ptr()), A, C.c_void_p(obs.data_ptr()), int(obs.shape[0]),
-            C.c_void_p(rewards.data_ptr()), C.c_void_p(done.data_ptr()), C.c_void_p(steps.data_ptr()), S, int(chains),
-            self._stream()))
+        if out_codes is not None:
+            assert out_codes.is_cuda and out_codes.is_contiguous() and out_codes.dtype == torch.uint8 and tuple(out_codes.shape) == (S, B, N)
+        io = _native.RolloutIO(T, actions.data_ptr(), A, obs.data_ptr(), int(obs.shape[0]),
+                               rewards.data_ptr() if rewards is not None else None,
+                               out_codes.data_ptr() if out_codes is not None else None, done.data_ptr(), steps.data_ptr(), S,
+                               int(chains))
+        _native.check(self._lib.mapf_env_rollout_ex(self._h, C.byref(io), self._stream()))
         return obs, rewards, done, steps
+
+    def set_autoreset(self, max_steps: int = config.max_steps, seed: int = 0, env_offset: int = 0, stride: Optional[int] = None,
+                      density: Optional[float] = None):
+        """Episode handling inside `rollout` (worker.py:390,422-428): a step that finds its environment finished (done, or
+        steps >= max_steps) re-generates the slot on the device instead of moving anybody -- the slot's n-th new instance
+        is Philox stream (seed, env_offset + n * stride + e), what `reset(mask={e}, seed, env_offset + n * stride)` draws
+        -- and emits the new episode's first observation with rewards 0 (code 5), done 0, steps 0.  `stride` = number of
+        environments of the whole job (default: this batch).  max_steps = 0 switches it off."""
+        dens = -1.0 if density is None else float(density)
+        _native.check(self._lib.mapf_env_set_autoreset(self._h, int(max_steps), C.c_uint64(seed), C.c_uint64(env_offset),
+                                                      C.c_uint64(stride if stride is not None else self.num_envs),
+                                                      C.c_float(dens), self._stream()))
+
+    def set_checks(self, check_unique: bool = True):
+        """Post-step uniqueness check of the agents' cells (environment.py:424-428) in every step; a violation raises
+        RuntimeError('unique') from check()."""
+        _native.check(self._lib.mapf_env_set_checks(self._h, int(bool(check_unique))))
 
     def rollout_plan(self, num_steps: int, action_slots: int, obs_slots: int, out_slots: int, chains: int = 0):
         """-> (chains, envs_per_chain, graph_period) mapf_env_rollout would use (graph_period 0 = direct launches)."""
@@ -206,10 +257,12 @@ class BatchedEnvironment:
         if hb is None:
             hb = dict(actions=torch.empty((B, N), dtype=torch.uint8, pin_memory=True),
                       rewards=torch.empty((B, N), dtype=torch.float32, pin_memory=True),
+                      codes=torch.empty((B, N), dtype=torch.uint8, pin_memory=True),
                       done=torch.empty((B,), dtype=torch.uint8, pin_memory=True),
                       steps=torch.empty((B,), dtype=torch.int32, pin_memory=True))
             hb.update({k + "_np": v.numpy() for k, v in list(hb.items())})
             hb["ptrs"] = tuple(C.c_void_p(hb[k].data_ptr()) for k in ("actions", "rewards", "done", "steps"))
+            hb["codes_ptr"] = C.c_void_p(hb["codes"].data_ptr())
             self._hb = hb
         if want_obs and "obs" not in hb:
             hb["obs"] = torch.empty((B, N, *self.OBS_SHAPE), dtype=torch.uint8, pin_memory=True)
@@ -231,28 +284,45 @@ class BatchedEnvironment:
         hb = self._host_buffers(want_obs)
         pa, pr, pd, ps = hb["ptrs"]
         torch = _torch()
-        if isinstance(actions, torch.Tensor):
-            # a page-locked uint8 CPU tensor (torch pin_memory) is read by the GPU in place: no staging copy
-            assert (actions.device.type == "cpu" and actions.dtype == torch.uint8 and actions.is_contiguous()
-                    and tuple(actions.shape) == (B, N)), "actions number"
-            ptr = actions.data_ptr()
-            known = hb.setdefault("pinned_ptrs", {})   # is_pinned() is a driver query: once per buffer
-            if ptr not in known:
-                if len(known) > 64:
-                    known.clear()
-                known[ptr] = C.c_void_p(ptr) if actions.is_pinned() else None
-            if known[ptr] is not None:
-                pa = known[ptr]
-            else:
-                np.copyto(hb["actions_np"], actions.numpy())
-        elif actions is not hb["actions_np"]:   # the caller may fill env.host_actions in place instead
-            a = np.asarray(actions)
-            assert a.shape == (B, N), "actions number"
-            np.copyto(hb["actions_np"], a, casting="unsafe")
+        pa = self._host_actions_ptr(actions, hb, pa)
         _native.check(self._lib.mapf_env_step_host(
             self._h, pa, hb["obs"].data_ptr() if want_obs else None, pr, pd, ps,
             C.c_void_p(device_obs.data_ptr()) if device_obs is not None else None, self._stream()))
         return (hb["obs_np"] if want_obs else None), hb["rewards_np"], hb["done_np"], hb["steps_np"]
+
+    def _host_actions_ptr(self, actions, hb, default_ptr):
+        """Pointer handed to the library for `actions`: a uint8 CPU tensor / the handle's own page-locked buffer is passed
+        in place (the library checks on every call whether it is page-locked and stages it otherwise); anything else is
+        copied into the handle's page-locked buffer first."""
+        torch = _torch()
+        B, N = self.num_envs, self.num_agents
+        if isinstance(actions, torch.Tensor):
+            assert (actions.device.type == "cpu" and actions.dtype == torch.uint8 and actions.is_contiguous()
+                    and tuple(actions.shape) == (B, N)), "actions number"
+            return C.c_void_p(actions.data_ptr())
+        if actions is not hb["actions_np"]:   # the caller may fill env.host_actions in place instead
+            a = np.asarray(actions)
+            assert a.shape == (B, N), "actions number"
+            np.copyto(hb["actions_np"], a, casting="unsafe")
+        return default_ptr
+
+    def step_host_codes(self, actions, device_obs):
+        """Throughput form of the host-buffer step (mapf_env_step_host_codes): reward CODES instead of fp32 rewards, one
+        fused kernel that publishes codes / done / steps straight into page-locked host memory; returns as soon as those
+        are final, while the observation (device tensor `device_obs`, required) is still being written on the current
+        stream.  Returns (codes uint8[B,N], done uint8[B], steps int32[B]) numpy VIEWS of page-locked buffers owned by this
+        object (overwritten by the next call); rewards = reward_table[codes], see `reward_table`."""
+        hb = self._host_buffers(False)
+        pa, _, pd, ps = hb["ptrs"]
+        pa = self._host_actions_ptr(actions, hb, pa)
+        _native.check(self._lib.mapf_env_step_host_codes(self._h, pa, hb["codes_ptr"], pd, ps, C.c_void_p(device_obs.data_ptr()),
+                                                        self._stream()))
+        return hb["codes_np"], hb["done_np"], hb["steps_np"]
+
+    @property
+    def reward_table(self) -> np.ndarray:
+        """float32[6]: reward of each reward code (config.REWARD_ORDER, then 0 for a reset step)."""
+        return np.asarray([float(self.reward_fn[k]) for k in config.REWARD_ORDER] + [0.0], dtype=np.float32)
 
     def check(self):
         """Synchronous: raise if a kernel latched an error (bad action -> AssertionError like the reference)."""
@@ -300,12 +370,12 @@ class BatchedEnvironment:
         torch = _torch()
         p = s = None
         if agents_pos is not None:
-            p = self._dev_u8(agents_pos, (self.num_envs, self.num_agents, 2))
+            p = self._coords_u8(agents_pos, (self.num_envs, self.num_agents, 2))
         if steps is not None:
             s = torch.as_tensor(steps, dtype=torch.int32).to(self.device).contiguous()
         _native.check(self._lib.mapf_env_set_state(self._h, C.c_void_p(p.data_ptr()) if p is not None else None,
                                                    C.c_void_p(s.data_ptr()) if s is not None else None, self._stream()))
-        torch.cuda.current_stream(self.device).synchronize()
+        self.check()   # synchronous; two agents on one cell -> RuntimeError('unique') (environment.py:424-428)
 
     def heuristic_distances(self, env_ids=None):
         """Recompute the BFS maps and return int32[n,N,L,L] distances (2147483647 = unreachable);

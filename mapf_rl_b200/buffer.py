@@ -94,9 +94,9 @@ class SumTree:
         idx = torch.as_tensor(idx, dtype=torch.int64).to(self.device).contiguous()
         prio = torch.as_tensor(prio, dtype=torch.float64).to(self.device).contiguous()
         assert idx.shape == prio.shape
+        # asynchronous on the current stream (device tensors are released stream-ordered by torch's allocator)
         _native.check(self._lib.mapf_per_update(self._h, C.c_void_p(idx.data_ptr()), C.c_void_p(prio.data_ptr()),
                                                 int(idx.numel()), self._stream()))
-        torch.cuda.current_stream(self.device).synchronize()
 
     def td_update(self, q_online, q_target_next, action, reward, done, steps, idx, old_ptr=0, ptr=0,
                   slot_steps=config.max_steps, gamma=0.99, alpha=config.prioritized_replay_alpha, q_online_next=None):
@@ -122,8 +122,60 @@ class SumTree:
             C.c_void_p(a.data_ptr()), C.c_void_p(r.data_ptr()), C.c_void_p(d.data_ptr()), C.c_void_p(s.data_ptr()),
             C.c_void_p(ix.data_ptr()), n, float(gamma), float(alpha), int(old_ptr), int(ptr), int(slot_steps),
             C.c_void_p(td.data_ptr()), C.c_void_p(pr.data_ptr()), self._stream()))
-        torch.cuda.current_stream(self.device).synchronize()
-        return td, pr
+        return td, pr   # asynchronous on the current stream
+
+    def cycle(self, update=None, sample_size: int = 0, uniforms=None, beta=None, old_ptr=0, ptr=0,
+              slot_steps=config.max_steps, gamma=0.99, alpha=config.prioritized_replay_alpha, out=None):
+        """One learner cycle in ONE launch (mapf_per_cycle): `update` = dict(q_online f32[n,5], q_target_next f32[n,5],
+        action i64[n], reward f32[n], done f32[n], steps f32[n], idx i64[n][, q_online_next]) of the batch that has just been
+        through the two Q forwards -> its priorities go into the tree; then `sample_size` new transitions are drawn from
+        the refreshed tree (uniforms f64[sample_size] in [0,1), default torch.rand) with IS weights when `beta` is given.
+        All tensors are float32 / int64 CUDA tensors, used as they are (no conversion, no synchronisation); `out` may hold
+        pre-allocated outputs (td, prio, idx, sample_prio, weights) for CUDA-graph capture.
+        Returns dict(td, prio, idx, sample_prio, weights) (entries None for an empty half)."""
+        torch = _torch()
+        out = dict(out or {})
+        a = _native.PerCycleArgs()
+        n = 0
+        if update is not None:
+            ix = update["idx"]
+            n = int(ix.numel())
+            for k in ("q_online", "q_target_next", "reward", "done", "steps"):
+                t = update[k]
+                assert t.is_cuda and t.dtype == torch.float32 and t.is_contiguous(), k
+            assert update["action"].dtype == torch.int64 and ix.dtype == torch.int64 and ix.is_contiguous()
+            assert tuple(update["q_online"].shape) == (n, 5) and tuple(update["q_target_next"].shape) == (n, 5)
+            out.setdefault("td", torch.empty(n, dtype=torch.float32, device=self.device))
+            out.setdefault("prio", torch.empty(n, dtype=torch.float32, device=self.device))
+            qn = update.get("q_online_next")
+            a.d_q_online, a.d_q_target_next = update["q_online"].data_ptr(), update["q_target_next"].data_ptr()
+            a.d_q_online_next = qn.data_ptr() if qn is not None else None
+            a.d_action, a.d_reward, a.d_done = update["action"].data_ptr(), update["reward"].data_ptr(), update["done"].data_ptr()
+            a.d_steps, a.d_idx = update["steps"].data_ptr(), ix.data_ptr()
+            a.d_td_out, a.d_prio_out = out["td"].data_ptr(), out["prio"].data_ptr()
+        a.n_update, a.gamma, a.alpha = n, float(gamma), float(alpha)
+        a.old_ptr, a.ptr, a.slot_steps = int(old_ptr), int(ptr), int(slot_steps)
+        m = int(sample_size)
+        if m > 0:
+            u = uniforms if uniforms is not None else torch.rand(m, dtype=torch.float64, device=self.device)
+            assert u.is_cuda and u.dtype == torch.float64 and u.is_contiguous() and u.numel() == m
+            out.setdefault("idx", torch.empty(m, dtype=torch.int64, device=self.device))
+            out.setdefault("sample_prio", torch.empty(m, dtype=torch.float64, device=self.device))
+            if beta is not None:
+                out.setdefault("weights", torch.empty(m, dtype=torch.float32, device=self.device))
+            a.d_uniforms, a.d_sample_idx_out, a.d_sample_prio_out = u.data_ptr(), out["idx"].data_ptr(), out["sample_prio"].data_ptr()
+            a.d_sample_weight_out = out["weights"].data_ptr() if beta is not None else None
+            out["_uniforms"] = u   # keep alive
+        a.n_sample, a.beta = m, float(beta or 0.0)
+        _native.check(self._lib.mapf_per_cycle(self._h, C.byref(a), self._stream()))
+        for k in ("td", "prio", "idx", "sample_prio", "weights"):
+            out.setdefault(k, None)
+        return out
+
+    def check(self):
+        """Synchronous: IndexError if an update was handed a leaf index outside [0, capacity) since the last call (numpy
+        raises at once; the kernels skip the entry and latch)."""
+        _native.check(self._lib.mapf_per_status(self._h, self._stream()))
 
     # -- reference numpy API -------------------------------------------------------------------
     def batch_sample(self, batch_size: int):  # buffer.py:56-78
@@ -137,6 +189,8 @@ class SumTree:
 
     def batch_update(self, idxes: np.ndarray, priorities: np.ndarray):  # buffer.py:95-105
         leaf = np.array(idxes, dtype=np.int64, copy=True)
+        if leaf.size and (leaf.min() < 0 or leaf.max() >= self.capacity):
+            raise IndexError("leaf index outside [0, capacity)")   # what numpy's fancy assignment raises (buffer.py:97)
         idxes += self.capacity - 1  # the reference mutates the caller's array (buffer.py:96)
         self.update_device(leaf, np.asarray(priorities, dtype=np.float64))
 
@@ -148,8 +202,10 @@ class SumTree:
 PrioritizedReplayTree = SumTree
 
 
-def actor_td_errors(rew, q, act, size, capacity=config.max_steps, device=None):
-    """Batched LocalBuffer.finish TD (buffer.py:170-177) on the device.
+def actor_td_errors(rew, q, act, size, capacity=config.max_steps, device=None, forward_steps=config.forward_steps,
+                    gamma=0.99):
+    """Batched LocalBuffer.finish TD (buffer.py:170-177) on the device: |sum_{j<forward_steps} gamma^j r[t+j] + max_a q - q[a_t]|
+    (the reference hard-codes 0.99 and reads config.forward_steps, buffer.py:174-175).
     rew float[E,capacity] (already fp16-rounded), q float32[E,capacity,5], act uint8[E,capacity], size int32[E]
     -> float64[E,capacity] CUDA tensor."""
     torch = _torch()
@@ -161,9 +217,10 @@ def actor_td_errors(rew, q, act, size, capacity=config.max_steps, device=None):
     E = int(s.numel())
     assert r.shape == (E, capacity) and qq.shape == (E, capacity, 5) and a.shape == (E, capacity)
     td = torch.empty((E, capacity), dtype=torch.float64, device=dev)
-    _native.check(_native.lib().mapf_actor_td(C.c_void_p(r.data_ptr()), C.c_void_p(qq.data_ptr()), C.c_void_p(a.data_ptr()),
-                                              C.c_void_p(s.data_ptr()), E, capacity, C.c_void_p(td.data_ptr()),
-                                              C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)))
+    _native.check(_native.lib().mapf_actor_td_n(C.c_void_p(r.data_ptr()), C.c_void_p(qq.data_ptr()), C.c_void_p(a.data_ptr()),
+                                                C.c_void_p(s.data_ptr()), E, capacity, int(forward_steps), float(gamma),
+                                                C.c_void_p(td.data_ptr()),
+                                                C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)))
     return td
 
 

@@ -10,16 +10,17 @@
 
 // launchers (other translation units)
 int mapf_launch_pack_load(mapf_env *, const int32_t *, int, const uint8_t *, const uint8_t *, const uint8_t *, cudaStream_t);
+int mapf_launch_validate_state(mapf_env *, const int32_t *, int, cudaStream_t);
 int mapf_launch_bfs(mapf_env *, const int32_t *, int, int32_t *, cudaStream_t);
-int mapf_launch_step(mapf_env *, const uint8_t *, uint8_t *, const int64_t *, float *, uint8_t *, int32_t *, cudaStream_t);
+int mapf_launch_step(mapf_env *, const uint8_t *, uint8_t *, const int64_t *, const StepOut &, cudaStream_t);
 int mapf_launch_observe(mapf_env *, uint8_t *, const int64_t *, uint8_t *, cudaStream_t);
-int mapf_launch_step_only(mapf_env *, const uint8_t *, float *, uint8_t *, int32_t *, cudaStream_t);
-int mapf_launch_step_range(mapf_env *, int, int, const uint8_t *, uint8_t *, float *, uint8_t *, int32_t *, cudaStream_t);
-int mapf_launch_rollout_persistent(mapf_env *, int, const uint8_t *, int, uint8_t *, int, float *, uint8_t *, int32_t *, int, int,
-                                   int, cudaStream_t);
+int mapf_launch_step_only(mapf_env *, const uint8_t *, const StepOut &, cudaStream_t);
+int mapf_launch_step_range(mapf_env *, int, int, const uint8_t *, uint8_t *, const StepOut &, cudaStream_t);
+int mapf_launch_rollout(mapf_env *, int, int, int, const uint8_t *, int, uint8_t *, int, const StepOut &, int, cudaStream_t);
+bool mapf_rollout_supported(const mapf_env *);
+void mapf_set_rollout_tuning(int, int, int, int);
 void mapf_set_step_tuning(int, int, int);
 int mapf_step_tuning_generation();
-void mapf_set_step_trace(unsigned long long *);
 int mapf_launch_unpack(mapf_env *, uint8_t *, uint8_t *, cudaStream_t);
 int mapf_launch_comm_mask(mapf_env *, int, uint8_t *, cudaStream_t);
 int mapf_launch_reset(mapf_env *, const uint8_t *, uint64_t, uint64_t, float, cudaStream_t);
@@ -28,7 +29,8 @@ int mapf_launch_per_sample(mapf_per *, const double *, int64_t, int64_t *, doubl
 int mapf_launch_per_td_update(mapf_per *, PerScratch *, const float *, const float *, const float *, const int64_t *,
                               const float *, const float *, const float *, const int64_t *, int64_t, float, double, int64_t,
                               int64_t, int64_t, float *, float *, cudaStream_t);
-int mapf_launch_actor_td(const float *, const float *, const uint8_t *, const int32_t *, int, int, double *, cudaStream_t);
+int mapf_launch_per_cycle(mapf_per *, PerScratch *, const mapf_per_cycle_args *, cudaStream_t);
+int mapf_launch_actor_td(const float *, const float *, const uint8_t *, const int32_t *, int, int, int, double, double *, cudaStream_t);
 int mapf_launch_replay_gather(const mapf_replay_view *, const int64_t *, int64_t, const mapf_replay_batch *, int32_t *, cudaStream_t);
 
 static thread_local std::string g_last_error;
@@ -79,14 +81,21 @@ T *host_device_alias(T *p)
     return static_cast<T *>(dptr);
 }
 
-// MAPF_STEP_HOST_MODE (measured on 8192 x 32 agents, profiles/e2e_modes.py):
-//   0  DMA copies either side of the fused kernel                                              109 us per call
-//   1  the fused kernel stores rewards / done / steps straight into the page-locked buffers    ~97 us
-//   2  ... and reads the actions in place (the 1 MB of PCIe writes stretches the kernel 33 -> 58 us)   87 us
-//   3  split: step kernel, then the observe kernel while the results are copied on a side stream     88 us
-//   4  the sequence of 3 captured once per buffer set and replayed with one cudaGraphLaunch (default) 78 us
-// Measured and dropped: the batch as 2 / 4 / 8 sub-batch chains, each {actions -> fused kernel -> results} on its own stream
-// inside the graph (105 / 124 / 160 us: every extra DMA node costs more than the overlap returns; profiles/r1_e2e_chains.log).
+// what a host pointer is RIGHT NOW (never cached: a page-locked buffer may have been freed and a pageable one mapped at the
+// same address since the last call); two driver queries of well under a microsecond each
+template <typename T>
+T *pinned_alias(T *p)
+{
+    if (!p || !host_is_pinned(p)) return nullptr;
+    return host_device_alias(p);
+}
+
+// MAPF_STEP_HOST_MODE: forms of mapf_env_step_host (fp32 rewards; measured on 8192 x 32 agents in round 1, profiles/):
+//   < 4  step kernel, then the observe kernel while the results are copied on a side stream, issued call by call   88 us
+//   4    the same sequence captured once per buffer set and replayed with one cudaGraphLaunch (default)           58-62 us
+// (dropped in round 2: DMA copies either side of the fused kernel 109 us; the fused kernel storing 1 MB of fp32 rewards
+// straight into host memory 87-97 us.)  The throughput form is mapf_env_step_host_codes: one fused kernel, u8 reward codes
+// published zero-copy, the call returns when the results -- not the observation stores -- are done.
 int &step_host_mode_ref()
 {
     static int m = [] {
@@ -180,8 +189,16 @@ int mapf_env_create(const mapf_env_config *cfg, mapf_env **out)
     if (rc == MAPF_OK) rc = dev_alloc(&env->navi, BN * d.navi_agent_stride, &total);
     if (rc == MAPF_OK) rc = dev_alloc(&env->steps, (size_t)d.B, &total);
     if (rc == MAPF_OK) rc = dev_alloc(&env->err, 1, &total);
+    if (rc == MAPF_OK) rc = dev_alloc(&env->ro_work, 2, &total);
+    if (rc == MAPF_OK) rc = dev_alloc(&env->ro_progress, (size_t)d.B, &total);
+    if (rc == MAPF_OK) rc = dev_alloc(&env->ro_episode, (size_t)d.B, &total);
+    if (rc == MAPF_OK) rc = dev_alloc(&env->pub_counter, 1, &total);
     if (rc == MAPF_OK) {
         cudaError_t e2 = cudaMemset(env->obst, 0, (size_t)d.B * d.obst_stride * 4);
+        if (e2 == cudaSuccess) e2 = cudaMemset(env->ro_work, 0, 16);
+        if (e2 == cudaSuccess) e2 = cudaMemset(env->ro_progress, 0, (size_t)d.B * 4);
+        if (e2 == cudaSuccess) e2 = cudaMemset(env->ro_episode, 0, (size_t)d.B * 4);
+        if (e2 == cudaSuccess) e2 = cudaMemset(env->pub_counter, 0, 4);
         if (e2 == cudaSuccess) e2 = cudaMemset(env->pos, 0, BN * 2);
         if (e2 == cudaSuccess) e2 = cudaMemset(env->goal, 0, BN * 2);
         if (e2 == cudaSuccess) e2 = cudaMemset(env->navi, 0, BN * d.navi_agent_stride * 4);
@@ -209,12 +226,17 @@ int mapf_env_destroy(mapf_env *env)
     cudaFree(env->navi);
     cudaFree(env->steps);
     cudaFree(env->err);
+    cudaFree(env->ro_work);
+    cudaFree(env->ro_progress);
+    cudaFree(env->ro_episode);
+    cudaFree(env->pub_counter);
     cudaFree(env->d_actions);
     cudaFree(env->d_obs);
     cudaFree(env->d_rewards);
     cudaFree(env->d_done);
     cudaFree(env->d_steps_out);
     if (env->h_pinned) cudaFreeHost(env->h_pinned);
+    if (env->h_flag) cudaFreeHost(const_cast<uint32_t *>(env->h_flag));
     for (auto &c : env->hg)
         if (c.exec) cudaGraphExecDestroy(c.exec);
     if (env->cap_stream) cudaStreamDestroy(env->cap_stream);
@@ -258,6 +280,8 @@ int mapf_env_load(mapf_env *env, const int32_t *d_env_ids, int32_t n, const uint
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     int rc = mapf_launch_pack_load(env, d_env_ids, n, d_maps, d_agents, d_goals, st);
     if (rc != MAPF_OK) return rc;
+    rc = mapf_launch_validate_state(env, d_env_ids, n, st);  // coordinates inside the map, one agent per cell
+    if (rc != MAPF_OK) return rc;
     return mapf_launch_bfs(env, d_env_ids, n, nullptr, st);
 }
 
@@ -273,27 +297,37 @@ int mapf_env_bfs_navi(mapf_env *env, const int32_t *d_env_ids, int32_t n, int32_
     return mapf_launch_bfs(env, d_env_ids, n, d_dist_out, static_cast<cudaStream_t>(stream));
 }
 
-int mapf_env_step_observe(mapf_env *env, const uint8_t *d_actions, uint8_t *d_obs, float *d_rewards, uint8_t *d_done,
-                          int32_t *d_steps, void *stream)
+int mapf_env_step_observe_ex(mapf_env *env, const uint8_t *d_actions, uint8_t *d_obs, const int64_t *d_obs_rows, float *d_rewards,
+                             uint8_t *d_codes, uint8_t *d_done, int32_t *d_steps, void *stream)
 {
     REQUIRE_ENV(env);
-    if (!d_actions || !d_obs || !d_rewards || !d_done) {
+    if (!d_actions || !d_obs || !d_done) {
         mapf_set_error("mapf_env_step_observe: NULL buffer");
         return MAPF_EINVAL;
     }
-    return mapf_launch_step(env, d_actions, d_obs, nullptr, d_rewards, d_done, d_steps, static_cast<cudaStream_t>(stream));
+    StepOut out;
+    out.rewards = d_rewards, out.codes = d_codes, out.done = d_done, out.steps = d_steps;
+    return mapf_launch_step(env, d_actions, d_obs, d_obs_rows, out, static_cast<cudaStream_t>(stream));
+}
+
+int mapf_env_step_observe(mapf_env *env, const uint8_t *d_actions, uint8_t *d_obs, float *d_rewards, uint8_t *d_done,
+                          int32_t *d_steps, void *stream)
+{
+    if (!d_rewards) {
+        mapf_set_error("mapf_env_step_observe: NULL buffer");
+        return MAPF_EINVAL;
+    }
+    return mapf_env_step_observe_ex(env, d_actions, d_obs, nullptr, d_rewards, nullptr, d_done, d_steps, stream);
 }
 
 int mapf_env_step_observe_rows(mapf_env *env, const uint8_t *d_actions, uint8_t *d_obs_base, const int64_t *d_obs_rows,
                                float *d_rewards, uint8_t *d_done, int32_t *d_steps, void *stream)
 {
-    REQUIRE_ENV(env);
-    if (!d_actions || !d_obs_base || !d_obs_rows || !d_rewards || !d_done) {
+    if (!d_obs_rows || !d_rewards) {
         mapf_set_error("mapf_env_step_observe_rows: NULL buffer");
         return MAPF_EINVAL;
     }
-    return mapf_launch_step(env, d_actions, d_obs_base, d_obs_rows, d_rewards, d_done, d_steps,
-                            static_cast<cudaStream_t>(stream));
+    return mapf_env_step_observe_ex(env, d_actions, d_obs_base, d_obs_rows, d_rewards, nullptr, d_done, d_steps, stream);
 }
 
 int mapf_env_observe_rows(mapf_env *env, uint8_t *d_obs_base, const int64_t *d_obs_rows, uint8_t *d_pos, void *stream)
@@ -317,36 +351,28 @@ int mapf_env_observe(mapf_env *env, uint8_t *d_obs, uint8_t *d_pos, void *stream
 }
 
 namespace {
-// How mapf_env_rollout runs T steps: S chains of `per` environments each; P > 0 when whole slot periods of P steps are
-// replayed from per-chain captured graphs.
+// How the chained form of mapf_env_rollout runs T steps: S chains of `per` environments each; P > 0 when whole slot periods
+// of P steps are replayed from per-chain captured graphs.
 struct RolloutPlan {
     int S, per, P;
     bool graphs;
 };
-// Process-wide knobs of the persistent rollout kernel (mapf_debug_rollout_tuning; read once from the environment):
-//   MAPF_ROLLOUT_PERSISTENT=0      never use it (chains of launches instead)
-//   MAPF_ROLLOUT_ENVS_PER_WARP=n   environments each resident warp takes through their T steps (0 = B / (16 warps per SM))
-//   MAPF_ROLLOUT_CTA_WARPS=1|2|4   warps per CTA (default 2)
-struct RolloutTuning {
-    int persistent, envs_per_warp, cta_warps;
-};
-RolloutTuning &rollout_tuning()
+// MAPF_ROLLOUT_PERSISTENT=0: never use the persistent kernel (chains of launches instead); the kernel's own knobs live in
+// mapf_rollout_kernels.cu (mapf_debug_rollout_tuning)
+int &rollout_persistent_ref()
 {
-    static RolloutTuning t = [] {
-        RolloutTuning r{1, 0, 2};
-        if (const char *s = std::getenv("MAPF_ROLLOUT_PERSISTENT")) r.persistent = std::atoi(s);
-        if (const char *s = std::getenv("MAPF_ROLLOUT_ENVS_PER_WARP")) r.envs_per_warp = std::atoi(s);
-        if (const char *s = std::getenv("MAPF_ROLLOUT_CTA_WARPS")) r.cta_warps = std::atoi(s);
-        return r;
+    static int v = [] {
+        const char *s = std::getenv("MAPF_ROLLOUT_PERSISTENT");
+        return s ? std::atoi(s) : 1;
     }();
-    return t;
+    return v;
 }
-bool rollout_persistent_enabled() { return rollout_tuning().persistent != 0; }
-// the persistent kernel serves the default request (chains = 0) on the hot geometry when the rollout is long enough for its
-// environment-major order to fill the GPU
-bool rollout_uses_persistent(const EnvDims &d, int T, int chains)
+// the persistent kernel serves the default request (chains = 0) for up to 64 agents; episode handling needs it
+bool rollout_uses_persistent(const mapf_env *env, int chains)
 {
-    return rollout_persistent_enabled() && chains == 0 && d.RW == 2 && d.K == 1 && d.B >= 2048 && T >= 16;
+    if (!mapf_rollout_supported(env)) return false;
+    if (env->ar_max_steps > 0) return true;
+    return rollout_persistent_ref() != 0 && chains == 0;
 }
 
 RolloutPlan rollout_plan(const EnvDims &d, int T, int action_slots, int obs_slots, int out_slots, int chains, bool capturing)
@@ -373,7 +399,7 @@ int mapf_env_rollout_plan(mapf_env *env, int32_t T, int32_t action_slots, int32_
         mapf_set_error("mapf_env_rollout_plan: T >= 0, slot counts >= 1 and 0 <= chains <= 16 required");
         return MAPF_EINVAL;
     }
-    if (rollout_uses_persistent(env->d, T, chains)) {  // one launch for the whole rollout
+    if (rollout_uses_persistent(env, chains)) {  // one launch for the whole rollout
         if (chains_out) *chains_out = 0;
         if (envs_per_chain_out) *envs_per_chain_out = env->d.B;
         if (graph_period_out) *graph_period_out = 0;
@@ -386,14 +412,14 @@ int mapf_env_rollout_plan(mapf_env *env, int32_t T, int32_t action_slots, int32_
     return MAPF_OK;
 }
 
-int mapf_env_rollout(mapf_env *env, int32_t T, const uint8_t *d_actions, int32_t action_slots, uint8_t *d_obs, int32_t obs_slots,
-                     float *d_rewards, uint8_t *d_done, int32_t *d_steps, int32_t out_slots, int32_t chains, void *stream)
+int mapf_env_rollout_ex(mapf_env *env, const mapf_rollout_io *io, void *stream)
 {
     REQUIRE_ENV(env);
-    if (!d_actions || !d_obs || !d_rewards || !d_done) {
+    if (!io || !io->d_actions || !io->d_obs || !io->d_done) {
         mapf_set_error("mapf_env_rollout: NULL buffer");
         return MAPF_EINVAL;
     }
+    const int T = io->T, action_slots = io->action_slots, obs_slots = io->obs_slots, out_slots = io->out_slots, chains = io->chains;
     if (T < 0 || action_slots < 1 || obs_slots < 1 || out_slots < 1 || chains < 0 || chains > MAPF_MAX_CHAINS) {
         mapf_set_error("mapf_env_rollout: T >= 0, slot counts >= 1 and 0 <= chains <= 16 required");
         return MAPF_EINVAL;
@@ -402,13 +428,21 @@ int mapf_env_rollout(mapf_env *env, int32_t T, const uint8_t *d_actions, int32_t
     const EnvDims &d = env->d;
     const size_t BN = (size_t)d.B * d.N;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if (rollout_uses_persistent(d, T, chains)) {
-        const int rc = mapf_launch_rollout_persistent(env, T, d_actions, action_slots, d_obs, obs_slots, d_rewards, d_done, d_steps,
-                                                      out_slots, rollout_tuning().envs_per_warp, rollout_tuning().cta_warps, st);
+    const uint8_t *d_actions = io->d_actions;
+    uint8_t *d_obs = io->d_obs;
+    StepOut ring;
+    ring.rewards = io->d_rewards, ring.codes = io->d_codes, ring.done = io->d_done, ring.steps = io->d_steps;
+    if (rollout_uses_persistent(env, chains)) {
+        const int rc = mapf_launch_rollout(env, 0, d.B, T, d_actions, action_slots, d_obs, obs_slots, ring, out_slots, st);
         if (rc != MAPF_EINVAL) return rc;
     }
-    // The launches of a long rollout repeat with period P = lcm(slot counts): those are captured once per chain into a
-    // graph of P kernel nodes and replayed (one cudaGraphLaunch per chain and period instead of P launches of ~4 us of
+    if (env->ar_max_steps > 0) {
+        mapf_set_error("mapf_env_rollout: episode handling (mapf_env_set_autoreset) is served by the persistent kernel only "
+                       "(up to 64 agents, per-warp state within shared memory)");
+        return MAPF_EINVAL;
+    }
+    // Chained form.  The launches of a long rollout repeat with period P = lcm(slot counts): those are captured once per chain
+    // into a graph of P kernel nodes and replayed (one cudaGraphLaunch per chain and period instead of P launches of ~4 us of
     // host time each, which bound 8 chains at 32 us per step); short rollouts and the tail are launched directly.
     cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
     MAPF_CUDA(cudaStreamIsCapturing(st, &cap));
@@ -417,8 +451,12 @@ int mapf_env_rollout(mapf_env *env, int32_t T, const uint8_t *d_actions, int32_t
     const bool graphs = pl.graphs;
     auto step_t = [&](int t, int e0, int e1, cudaStream_t q) -> int {
         const size_t sa = (size_t)(t % action_slots), so = (size_t)(t % obs_slots), sr = (size_t)(t % out_slots);
-        return mapf_launch_step_range(env, e0, e1, d_actions + sa * BN, d_obs + so * BN * MAPF_OBS_BYTES_PER_AGENT, d_rewards + sr * BN,
-                                      d_done + sr * d.B, d_steps ? d_steps + sr * d.B : nullptr, q);
+        StepOut o;
+        o.rewards = ring.rewards ? ring.rewards + sr * BN : nullptr;
+        o.codes = ring.codes ? ring.codes + sr * BN : nullptr;
+        o.done = ring.done + sr * d.B;
+        o.steps = ring.steps ? ring.steps + sr * d.B : nullptr;
+        return mapf_launch_step_range(env, e0, e1, d_actions + sa * BN, d_obs + so * BN * MAPF_OBS_BYTES_PER_AGENT, o, q);
     };
     if (S == 1) {
         for (int t = 0; t < T; ++t) {
@@ -443,9 +481,9 @@ int mapf_env_rollout(mapf_env *env, int32_t T, const uint8_t *d_actions, int32_t
         mapf_env::RolloutGraph *g = nullptr;
         const int gen = mapf_step_tuning_generation();
         for (auto &c : env->rg)
-            if (c.exec[0] && c.act == d_actions && c.obs == d_obs && c.rew == d_rewards && c.done == d_done && c.steps == d_steps &&
-                c.action_slots == action_slots && c.obs_slots == obs_slots && c.out_slots == out_slots && c.S == S && c.P == P &&
-                c.tuning_gen == gen)
+            if (c.exec[0] && c.act == d_actions && c.obs == d_obs && c.rew == ring.rewards && c.codes == ring.codes && c.done == ring.done &&
+                c.steps == ring.steps && c.action_slots == action_slots && c.obs_slots == obs_slots && c.out_slots == out_slots && c.S == S &&
+                c.P == P && c.tuning_gen == gen)
                 g = &c;
         if (!g) {
             g = &env->rg[env->rg_next];
@@ -476,7 +514,7 @@ int mapf_env_rollout(mapf_env *env, int32_t T, const uint8_t *d_actions, int32_t
                         x = nullptr;
                     }
             } else {
-                g->act = d_actions, g->obs = d_obs, g->rew = d_rewards, g->done = d_done, g->steps = d_steps;
+                g->act = d_actions, g->obs = d_obs, g->rew = ring.rewards, g->codes = ring.codes, g->done = ring.done, g->steps = ring.steps;
                 g->action_slots = action_slots, g->obs_slots = obs_slots, g->out_slots = out_slots, g->S = S, g->P = P, g->tuning_gen = gen;
             }
         }
@@ -503,6 +541,46 @@ int mapf_env_rollout(mapf_env *env, int32_t T, const uint8_t *d_actions, int32_t
     return rc;
 }
 
+int mapf_env_rollout(mapf_env *env, int32_t T, const uint8_t *d_actions, int32_t action_slots, uint8_t *d_obs, int32_t obs_slots,
+                     float *d_rewards, uint8_t *d_done, int32_t *d_steps, int32_t out_slots, int32_t chains, void *stream)
+{
+    if (!d_rewards) {
+        mapf_set_error("mapf_env_rollout: NULL buffer");
+        return MAPF_EINVAL;
+    }
+    mapf_rollout_io io{};
+    io.T = T, io.d_actions = d_actions, io.action_slots = action_slots, io.d_obs = d_obs, io.obs_slots = obs_slots;
+    io.d_rewards = d_rewards, io.d_codes = nullptr, io.d_done = d_done, io.d_steps = d_steps, io.out_slots = out_slots, io.chains = chains;
+    return mapf_env_rollout_ex(env, &io, stream);
+}
+
+int mapf_env_set_autoreset(mapf_env *env, int32_t max_steps, uint64_t seed, uint64_t env_offset, uint64_t stride, float density,
+                           void *stream)
+{
+    REQUIRE_ENV(env);
+    if (max_steps < 0 || density >= 1.0f) {
+        mapf_set_error("mapf_env_set_autoreset: max_steps >= 0 and density < 1 required");
+        return MAPF_EINVAL;
+    }
+    if (max_steps > 0 && !mapf_rollout_supported(env)) {
+        mapf_set_error("mapf_env_set_autoreset: episode handling is served by the persistent kernel only (up to 64 agents)");
+        return MAPF_EINVAL;
+    }
+    env->ar_max_steps = max_steps;
+    env->ar_seed = seed, env->ar_offset = env_offset, env->ar_stride = stride ? stride : (uint64_t)env->d.B;
+    env->ar_density = density;
+    MAPF_CUDA(cudaMemsetAsync(env->ro_episode, 0, (size_t)env->d.B * 4, static_cast<cudaStream_t>(stream)));
+    return MAPF_OK;
+}
+
+int mapf_env_set_checks(mapf_env *env, int32_t check_unique)
+{
+    REQUIRE_ENV(env);
+    env->check_unique = check_unique != 0;
+    env->checks_gen++;  // captured step_host graphs carry the old flag
+    return MAPF_OK;
+}
+
 int mapf_env_step_host(mapf_env *env, const uint8_t *h_actions, uint8_t *h_obs, float *h_rewards, uint8_t *h_done,
                        int32_t *h_steps, uint8_t *d_obs_opt, void *stream)
 {
@@ -520,10 +598,10 @@ int mapf_env_step_host(mapf_env *env, const uint8_t *h_actions, uint8_t *h_obs, 
         if (rc == MAPF_OK) rc = dev_alloc(&env->d_rewards, BN, &total);
         if (rc == MAPF_OK) rc = dev_alloc(&env->d_done, (size_t)d.B, &total);
         if (rc == MAPF_OK) rc = dev_alloc(&env->d_steps_out, (size_t)d.B, &total);
-        if (rc == MAPF_OK) {
-            cudaError_t e = cudaMallocHost(reinterpret_cast<void **>(&env->h_pinned), BN + BN * 4 + (size_t)d.B * 5 + 64);
-            if (e != cudaSuccess) rc = mapf_cuda_fail(e, "cudaMallocHost");
-        }
+    }
+    if (rc == MAPF_OK && !env->h_pinned) {
+        cudaError_t e = cudaMallocHost(reinterpret_cast<void **>(&env->h_pinned), BN + BN * 4 + (size_t)d.B * 5 + 128);
+        if (e != cudaSuccess) rc = mapf_cuda_fail(e, "cudaMallocHost");
     }
     if (rc == MAPF_OK && !d_obs_opt && !env->d_obs) rc = dev_alloc(&env->d_obs, BN * MAPF_OBS_BYTES_PER_AGENT, &total);
     env->arena_bytes = total;
@@ -536,174 +614,163 @@ int mapf_env_step_host(mapf_env *env, const uint8_t *h_actions, uint8_t *h_obs, 
     float *pin_rew = reinterpret_cast<float *>(env->h_pinned + ((BN + 15) & ~(size_t)15));
     int32_t *pin_steps = reinterpret_cast<int32_t *>(pin_rew + BN);
     uint8_t *pin_done = reinterpret_cast<uint8_t *>(pin_steps + d.B);
-    // page-locked caller buffers are used as DMA endpoints directly; pageable ones go through the handle's
-    // pinned staging area (one extra host memcpy each way)
-    const void *keys[4] = {h_actions, h_rewards, h_done, h_steps};
-    for (int i = 0; i < 4; ++i) {
-        if (keys[i] != env->hc_key[i]) {
-            env->hc_key[i] = keys[i];
-            // an actor that rotates over a few page-locked action buffers pays the two driver queries once per buffer
-            mapf_env::PtrInfo *hit = nullptr;
-            for (auto &c : env->ptr_cache)
-                if (c.key == keys[i] && c.key) hit = &c;
-            if (!hit) {
-                hit = &env->ptr_cache[env->ptr_cache_next];
-                env->ptr_cache_next = (env->ptr_cache_next + 1) % 32;
-                hit->key = keys[i];
-                hit->pinned = keys[i] && host_is_pinned(keys[i]);
-                hit->alias = hit->pinned ? host_device_alias(const_cast<void *>(keys[i])) : nullptr;
-            }
-            env->hc_pinned[i] = hit->pinned;
-            env->hc_alias[i] = hit->alias;
-        }
-    }
-    const bool act_direct = env->hc_pinned[0];
-    const bool out_direct = env->hc_pinned[1] && env->hc_pinned[2] && (!h_steps || env->hc_pinned[3]);
+    // page-locked caller buffers are used in place; pageable ones go through the handle's pinned staging area (one extra
+    // host memcpy each way)
+    const uint8_t *act_alias = pinned_alias(h_actions);
+    const bool out_direct = host_is_pinned(h_rewards) && host_is_pinned(h_done) && (!h_steps || host_is_pinned(h_steps));
     const uint8_t *src_act = h_actions;
-    if (!act_direct) {
+    if (!act_alias) {
         std::memcpy(pin_act, h_actions, BN);
         src_act = pin_act;
+        act_alias = host_device_alias(pin_act);
     }
     float *dst_rew = out_direct ? h_rewards : pin_rew;
     uint8_t *dst_done = out_direct ? h_done : pin_done;
-    int32_t *dst_steps = out_direct ? h_steps : pin_steps;
-    const int mode = step_host_mode();
-    if (mode >= 3) {
-        // split: step kernel -> {observe kernel on `st`  ||  result copies on the side stream} -> join
-        if (!env->side_stream) {
-            MAPF_CUDA(cudaStreamCreateWithFlags(&env->side_stream, cudaStreamNonBlocking));
-            MAPF_CUDA(cudaEventCreateWithFlags(&env->ev_stepped, cudaEventDisableTiming));
-            MAPF_CUDA(cudaEventCreateWithFlags(&env->ev_copied, cudaEventDisableTiming));
+    int32_t *dst_steps = h_steps ? (out_direct ? h_steps : pin_steps) : nullptr;
+    // split: step kernel -> {observe kernel on `st`  ||  result copies on the side stream} -> join
+    if (!env->side_stream) {
+        MAPF_CUDA(cudaStreamCreateWithFlags(&env->side_stream, cudaStreamNonBlocking));
+        MAPF_CUDA(cudaEventCreateWithFlags(&env->ev_stepped, cudaEventDisableTiming));
+        MAPF_CUDA(cudaEventCreateWithFlags(&env->ev_copied, cudaEventDisableTiming));
+    }
+    // issues the whole sequence on `q` (forking to the side stream and joining back)
+    auto enqueue = [&](cudaStream_t q) -> int {
+        const uint8_t *a = act_alias;  // read in place over PCIe
+        if (!a) {
+            MAPF_CUDA(cudaMemcpyAsync(env->d_actions, src_act, BN, cudaMemcpyHostToDevice, q));
+            a = env->d_actions;
         }
-        static const bool dma_actions = std::getenv("MAPF_STEP_HOST_DMA_ACTIONS") != nullptr;  // probe: H2D copy node instead
-        const uint8_t *act_dev = act_direct && !dma_actions ? static_cast<const uint8_t *>(env->hc_alias[0]) : nullptr;  // read in place over PCIe
-        // issues the whole sequence on `q` (forking to the side stream and joining back)
-        // MAPF_STEP_HOST_TRACE=1 (mode 3 only): timing events between the phases, printed to stderr after the sync
-        static const bool trace = std::getenv("MAPF_STEP_HOST_TRACE") != nullptr;
-        static cudaEvent_t tev[5] = {};
-        const bool tracing = trace && mode == 3;
-        if (tracing && !tev[0])
-            for (auto &e : tev) MAPF_CUDA(cudaEventCreate(&e));
-        auto enqueue = [&](cudaStream_t q) -> int {
-            if (tracing) MAPF_CUDA(cudaEventRecord(tev[0], q));
-            const uint8_t *a = act_dev;
-            if (!a) {
-                MAPF_CUDA(cudaMemcpyAsync(env->d_actions, src_act, BN, cudaMemcpyHostToDevice, q));
-                a = env->d_actions;
-            }
-            int r = mapf_launch_step_only(env, a, env->d_rewards, env->d_done, env->d_steps_out, q);
-            if (r != MAPF_OK) return r;
-            if (tracing) MAPF_CUDA(cudaEventRecord(tev[1], q));
-            MAPF_CUDA(cudaEventRecord(env->ev_stepped, q));
-            MAPF_CUDA(cudaStreamWaitEvent(env->side_stream, env->ev_stepped, 0));
-            MAPF_CUDA(cudaMemcpyAsync(dst_rew, env->d_rewards, BN * 4, cudaMemcpyDeviceToHost, env->side_stream));
-            if (dst_steps)
-                MAPF_CUDA(cudaMemcpyAsync(dst_steps, env->d_steps_out, (size_t)d.B * 4, cudaMemcpyDeviceToHost, env->side_stream));
-            MAPF_CUDA(cudaMemcpyAsync(dst_done, env->d_done, (size_t)d.B, cudaMemcpyDeviceToHost, env->side_stream));
-            if (tracing) MAPF_CUDA(cudaEventRecord(tev[2], env->side_stream));
-            MAPF_CUDA(cudaEventRecord(env->ev_copied, env->side_stream));
-            r = mapf_launch_observe(env, obs_dev, nullptr, nullptr, q);
-            if (r != MAPF_OK) return r;
-            if (tracing) MAPF_CUDA(cudaEventRecord(tev[3], q));
-            if (h_obs) MAPF_CUDA(cudaMemcpyAsync(h_obs, obs_dev, BN * MAPF_OBS_BYTES_PER_AGENT, cudaMemcpyDeviceToHost, q));
-            MAPF_CUDA(cudaStreamWaitEvent(q, env->ev_copied, 0));
-            if (tracing) MAPF_CUDA(cudaEventRecord(tev[4], q));
-            return MAPF_OK;
-        };
-        if (mode >= 4) {
-            // one cudaGraphLaunch instead of nine stream calls: the sequence is captured per buffer set
-            mapf_env::HostGraph *g = nullptr;
-            for (auto &c : env->hg)
-                if (c.exec && c.act == src_act && c.rew == dst_rew && c.done == dst_done && c.steps == dst_steps && c.hobs == h_obs &&
-                    c.obs_dev == obs_dev && c.mode == mode)
-                    g = &c;
-            if (!g) {
-                if (!env->cap_stream) MAPF_CUDA(cudaStreamCreateWithFlags(&env->cap_stream, cudaStreamNonBlocking));
-                g = &env->hg[env->hg_next];
-                env->hg_next = (env->hg_next + 1) % 32;
-                if (g->exec) {
-                    cudaGraphExecDestroy(g->exec);
-                    g->exec = nullptr;
-                }
-                cudaGraph_t graph = nullptr;
-                MAPF_CUDA(cudaStreamBeginCapture(env->cap_stream, cudaStreamCaptureModeThreadLocal));
-                rc = enqueue(env->cap_stream);
-                cudaError_t ce = cudaStreamEndCapture(env->cap_stream, &graph);
-                if (rc != MAPF_OK) {
-                    if (graph) cudaGraphDestroy(graph);
-                    return rc;
-                }
-                if (ce != cudaSuccess) return mapf_cuda_fail(ce, "cudaStreamEndCapture");
-                ce = cudaGraphInstantiate(&g->exec, graph, 0);
-                cudaGraphDestroy(graph);
-                if (ce != cudaSuccess) return mapf_cuda_fail(ce, "cudaGraphInstantiate");
-                g->act = src_act, g->rew = dst_rew, g->done = dst_done, g->steps = dst_steps, g->hobs = h_obs, g->obs_dev = obs_dev, g->mode = mode;
-            }
-            MAPF_CUDA(cudaGraphLaunch(g->exec, st));
-        } else {
-            rc = enqueue(st);
-            if (rc != MAPF_OK) return rc;
-        }
-        MAPF_CUDA(cudaStreamSynchronize(st));
-        if (tracing) {
-            float t[4] = {};
-            for (int i = 0; i < 4; ++i) cudaEventElapsedTime(&t[i], tev[0], tev[i + 1]);
-            std::fprintf(stderr, "step_host trace (us since start): step kernel done %.1f, copies done %.1f, observe done %.1f, joined %.1f\n",
-                         t[0] * 1e3f, t[1] * 1e3f, t[2] * 1e3f, t[3] * 1e3f);
-        }
-        if (!out_direct) {
-            std::memcpy(h_rewards, pin_rew, BN * 4);
-            std::memcpy(h_done, pin_done, (size_t)d.B);
-            if (h_steps) std::memcpy(h_steps, pin_steps, (size_t)d.B * 4);
-        }
+        StepOut o;
+        o.rewards = env->d_rewards, o.done = env->d_done, o.steps = env->d_steps_out;
+        int r = mapf_launch_step_only(env, a, o, q);
+        if (r != MAPF_OK) return r;
+        MAPF_CUDA(cudaEventRecord(env->ev_stepped, q));
+        MAPF_CUDA(cudaStreamWaitEvent(env->side_stream, env->ev_stepped, 0));
+        MAPF_CUDA(cudaMemcpyAsync(dst_rew, env->d_rewards, BN * 4, cudaMemcpyDeviceToHost, env->side_stream));
+        if (dst_steps)
+            MAPF_CUDA(cudaMemcpyAsync(dst_steps, env->d_steps_out, (size_t)d.B * 4, cudaMemcpyDeviceToHost, env->side_stream));
+        MAPF_CUDA(cudaMemcpyAsync(dst_done, env->d_done, (size_t)d.B, cudaMemcpyDeviceToHost, env->side_stream));
+        MAPF_CUDA(cudaEventRecord(env->ev_copied, env->side_stream));
+        r = mapf_launch_observe(env, obs_dev, nullptr, nullptr, q);
+        if (r != MAPF_OK) return r;
+        if (h_obs) MAPF_CUDA(cudaMemcpyAsync(h_obs, obs_dev, BN * MAPF_OBS_BYTES_PER_AGENT, cudaMemcpyDeviceToHost, q));
+        MAPF_CUDA(cudaStreamWaitEvent(q, env->ev_copied, 0));
         return MAPF_OK;
-    }
-    // zero-copy: the kernel's own loads / stores reach the host buffers (no DMA launches around the kernel)
-    float *zc_rew = nullptr;
-    uint8_t *zc_done = nullptr;
-    int32_t *zc_steps = nullptr;
-    const uint8_t *zc_act = nullptr;
-    if (mode >= 1) {
-        if (out_direct) {
-            zc_rew = static_cast<float *>(env->hc_alias[1]);
-            zc_done = static_cast<uint8_t *>(env->hc_alias[2]);
-            zc_steps = static_cast<int32_t *>(env->hc_alias[3]);
-        } else {
-            if (!env->pin_alias) env->pin_alias = host_device_alias(env->h_pinned);
-            if (env->pin_alias) {
-                zc_rew = reinterpret_cast<float *>(env->pin_alias + (reinterpret_cast<uint8_t *>(pin_rew) - env->h_pinned));
-                zc_done = env->pin_alias + (pin_done - env->h_pinned);
-                zc_steps = reinterpret_cast<int32_t *>(env->pin_alias + (reinterpret_cast<uint8_t *>(pin_steps) - env->h_pinned));
+    };
+    if (step_host_mode() >= 4) {
+        // one cudaGraphLaunch instead of nine stream calls: the sequence is captured per buffer set
+        const int gen = mapf_step_tuning_generation() * 65536 + env->checks_gen;
+        mapf_env::HostGraph *g = nullptr;
+        for (auto &c : env->hg)
+            if (c.exec && c.act == (const void *)act_alias && c.rew == dst_rew && c.done == dst_done && c.steps == dst_steps && c.hobs == h_obs &&
+                c.obs_dev == obs_dev && c.gen == gen)
+                g = &c;
+        if (!g) {
+            if (!env->cap_stream) MAPF_CUDA(cudaStreamCreateWithFlags(&env->cap_stream, cudaStreamNonBlocking));
+            g = &env->hg[env->hg_next];
+            env->hg_next = (env->hg_next + 1) % 32;
+            if (g->exec) {
+                cudaGraphExecDestroy(g->exec);
+                g->exec = nullptr;
             }
+            cudaGraph_t graph = nullptr;
+            MAPF_CUDA(cudaStreamBeginCapture(env->cap_stream, cudaStreamCaptureModeThreadLocal));
+            rc = enqueue(env->cap_stream);
+            cudaError_t ce = cudaStreamEndCapture(env->cap_stream, &graph);
+            if (rc != MAPF_OK) {
+                if (graph) cudaGraphDestroy(graph);
+                return rc;
+            }
+            if (ce != cudaSuccess) return mapf_cuda_fail(ce, "cudaStreamEndCapture");
+            ce = cudaGraphInstantiate(&g->exec, graph, 0);
+            cudaGraphDestroy(graph);
+            if (ce != cudaSuccess) return mapf_cuda_fail(ce, "cudaGraphInstantiate");
+            g->act = act_alias, g->rew = dst_rew, g->done = dst_done, g->steps = dst_steps, g->hobs = h_obs, g->obs_dev = obs_dev, g->gen = gen;
         }
-        if (mode >= 2) {
-            if (act_direct) zc_act = static_cast<const uint8_t *>(env->hc_alias[0]);
-            else if (env->pin_alias) zc_act = env->pin_alias;
-        }
-    }
-    if (zc_rew && zc_done && (zc_steps || !dst_steps)) {
-        if (!zc_act) MAPF_CUDA(cudaMemcpyAsync(env->d_actions, src_act, BN, cudaMemcpyHostToDevice, st));
-        rc = mapf_launch_step(env, zc_act ? zc_act : env->d_actions, obs_dev, nullptr, zc_rew, zc_done, dst_steps ? zc_steps : nullptr, st);
+        MAPF_CUDA(cudaGraphLaunch(g->exec, st));
+    } else {
+        rc = enqueue(st);
         if (rc != MAPF_OK) return rc;
-        if (h_obs) MAPF_CUDA(cudaMemcpyAsync(h_obs, obs_dev, BN * MAPF_OBS_BYTES_PER_AGENT, cudaMemcpyDeviceToHost, st));
-        MAPF_CUDA(cudaStreamSynchronize(st));
-        if (!out_direct) {
-            std::memcpy(h_rewards, pin_rew, BN * 4);
-            std::memcpy(h_done, pin_done, (size_t)d.B);
-            if (h_steps) std::memcpy(h_steps, pin_steps, (size_t)d.B * 4);
-        }
-        return MAPF_OK;
     }
-    MAPF_CUDA(cudaMemcpyAsync(env->d_actions, src_act, BN, cudaMemcpyHostToDevice, st));
-    rc = mapf_launch_step(env, env->d_actions, obs_dev, nullptr, env->d_rewards, env->d_done, env->d_steps_out, st);
-    if (rc != MAPF_OK) return rc;
-    MAPF_CUDA(cudaMemcpyAsync(dst_rew, env->d_rewards, BN * 4, cudaMemcpyDeviceToHost, st));
-    if (dst_steps) MAPF_CUDA(cudaMemcpyAsync(dst_steps, env->d_steps_out, (size_t)d.B * 4, cudaMemcpyDeviceToHost, st));
-    MAPF_CUDA(cudaMemcpyAsync(dst_done, env->d_done, (size_t)d.B, cudaMemcpyDeviceToHost, st));
-    if (h_obs) MAPF_CUDA(cudaMemcpyAsync(h_obs, obs_dev, BN * MAPF_OBS_BYTES_PER_AGENT, cudaMemcpyDeviceToHost, st));
     MAPF_CUDA(cudaStreamSynchronize(st));
     if (!out_direct) {
         std::memcpy(h_rewards, pin_rew, BN * 4);
+        std::memcpy(h_done, pin_done, (size_t)d.B);
+        if (h_steps) std::memcpy(h_steps, pin_steps, (size_t)d.B * 4);
+    }
+    return MAPF_OK;
+}
+
+int mapf_env_step_host_codes(mapf_env *env, const uint8_t *h_actions, uint8_t *h_codes, uint8_t *h_done, int32_t *h_steps,
+                             uint8_t *d_obs, void *stream)
+{
+    REQUIRE_ENV(env);
+    if (!h_actions || !h_codes || !h_done || !d_obs) {
+        mapf_set_error("mapf_env_step_host_codes: NULL buffer");
+        return MAPF_EINVAL;
+    }
+    const EnvDims &d = env->d;
+    const size_t BN = (size_t)d.B * d.N;
+    if (!env->h_pinned) {
+        cudaError_t e = cudaMallocHost(reinterpret_cast<void **>(&env->h_pinned), BN + BN * 4 + (size_t)d.B * 5 + 128);
+        if (e != cudaSuccess) return mapf_cuda_fail(e, "cudaMallocHost");
+    }
+    if (!env->h_flag) {
+        void *flag = nullptr;
+        cudaError_t e = cudaMallocHost(&flag, 64);
+        if (e != cudaSuccess) return mapf_cuda_fail(e, "cudaMallocHost");
+        env->h_flag = static_cast<volatile uint32_t *>(flag);
+        *env->h_flag = 0;
+        env->d_flag = host_device_alias(const_cast<uint32_t *>(env->h_flag));
+        if (!env->d_flag) {
+            mapf_set_error("mapf_env_step_host_codes: page-locked host memory is not mapped into the device address space");
+            return MAPF_ECUDA;
+        }
+    }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    // staging layout for pageable caller buffers: actions u8[BN] | pad | codes u8[BN] | pad | steps i32[B] | done u8[B]
+    uint8_t *pin_act = env->h_pinned;
+    uint8_t *pin_codes = env->h_pinned + ((BN + 15) & ~(size_t)15);
+    int32_t *pin_steps = reinterpret_cast<int32_t *>(pin_codes + ((BN + 15) & ~(size_t)15));
+    uint8_t *pin_done = reinterpret_cast<uint8_t *>(pin_steps + d.B);
+    const uint8_t *act_alias = pinned_alias(h_actions);
+    if (!act_alias) {
+        std::memcpy(pin_act, h_actions, BN);
+        act_alias = host_device_alias(pin_act);
+    }
+    uint8_t *codes_alias = pinned_alias(h_codes), *done_alias = pinned_alias(h_done);
+    int32_t *steps_alias = h_steps ? pinned_alias(h_steps) : nullptr;
+    const bool out_direct = codes_alias && done_alias && (!h_steps || steps_alias);
+    if (!out_direct) {
+        codes_alias = host_device_alias(pin_codes), done_alias = host_device_alias(pin_done);
+        steps_alias = h_steps ? host_device_alias(pin_steps) : nullptr;
+    }
+    if (!act_alias || !codes_alias || !done_alias) {
+        mapf_set_error("mapf_env_step_host_codes: page-locked host memory is not mapped into the device address space");
+        return MAPF_ECUDA;
+    }
+    StepOut o;
+    o.codes = codes_alias, o.done = done_alias, o.steps = steps_alias;
+    o.pub.counter = env->pub_counter;
+    o.pub.flag = env->d_flag;
+    o.pub.seq = ++env->pub_seq ? env->pub_seq : ++env->pub_seq;  // never 0
+    const int rc = mapf_launch_step(env, act_alias, d_obs, nullptr, o, st);
+    if (rc != MAPF_OK) return rc;
+    // wait for the flag, not for the kernel: the observation stores keep draining on `st`
+    const uint32_t want = o.pub.seq;
+    unsigned spins = 0;
+    while (*env->h_flag != want) {
+        if ((++spins & 0x3fff) == 0) {  // every ~16k polls: has the stream died (launch failure, sticky error)?
+            const cudaError_t q = cudaStreamQuery(st);
+            if (q != cudaErrorNotReady && q != cudaSuccess) return mapf_cuda_fail(q, "mapf_env_step_host_codes (kernel)");
+            if (q == cudaSuccess && *env->h_flag != want) {
+                mapf_set_error("mapf_env_step_host_codes: the kernel finished without raising the host flag");
+                return MAPF_ECUDA;
+            }
+        }
+    }
+    if (!out_direct) {
+        std::memcpy(h_codes, pin_codes, BN);
         std::memcpy(h_done, pin_done, (size_t)d.B);
         if (h_steps) std::memcpy(h_steps, pin_steps, (size_t)d.B * 4);
     }
@@ -716,12 +783,10 @@ int mapf_debug_step_tuning(int32_t variant, int32_t flags, int32_t ctas_per_sm)
     return MAPF_OK;
 }
 
-int mapf_debug_rollout_tuning(int32_t persistent, int32_t envs_per_warp, int32_t cta_warps)
+int mapf_debug_rollout_tuning(int32_t persistent, int32_t warps_per_sm, int32_t chunk, int32_t store_mode, int32_t stagger_ns)
 {
-    RolloutTuning &t = rollout_tuning();
-    if (persistent >= 0) t.persistent = persistent;
-    if (envs_per_warp >= 0) t.envs_per_warp = envs_per_warp;
-    if (cta_warps >= 0) t.cta_warps = cta_warps;
+    if (persistent >= 0) rollout_persistent_ref() = persistent;
+    mapf_set_rollout_tuning(warps_per_sm, chunk, store_mode, stagger_ns);
     return MAPF_OK;
 }
 
@@ -729,12 +794,6 @@ int mapf_debug_step_host_mode(int32_t mode)
 {
     if (mode >= 0) step_host_mode_ref() = mode;
     return step_host_mode_ref();
-}
-
-int mapf_debug_step_trace(uint64_t *d_trace)
-{
-    mapf_set_step_trace(reinterpret_cast<unsigned long long *>(d_trace));
-    return MAPF_OK;
 }
 
 int mapf_env_comm_mask(mapf_env *env, int32_t max_comm_agents, uint8_t *d_mask_out, void *stream)
@@ -763,7 +822,11 @@ int mapf_env_set_state(mapf_env *env, const uint8_t *d_pos, const int32_t *d_ste
 {
     REQUIRE_ENV(env);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if (d_pos) MAPF_CUDA(cudaMemcpyAsync(env->pos, d_pos, (size_t)env->d.B * env->d.N * 2, cudaMemcpyDeviceToDevice, st));
+    if (d_pos) {
+        MAPF_CUDA(cudaMemcpyAsync(env->pos, d_pos, (size_t)env->d.B * env->d.N * 2, cudaMemcpyDeviceToDevice, st));
+        const int rc = mapf_launch_validate_state(env, nullptr, env->d.B, st);  // clamps + latches MAPF_ESTATE
+        if (rc != MAPF_OK) return rc;
+    }
     if (d_steps) MAPF_CUDA(cudaMemcpyAsync(env->steps, d_steps, (size_t)env->d.B * 4, cudaMemcpyDeviceToDevice, st));
     return MAPF_OK;
 }
@@ -779,6 +842,10 @@ int mapf_env_status(mapf_env *env, void *stream)
         MAPF_CUDA(cudaMemsetAsync(env->err, 0, 4, st));
         MAPF_CUDA(cudaStreamSynchronize(st));
     }
+    if (bits & MAPF_ERRBIT_STATE) {
+        mapf_set_error("invalid state: coordinate outside the map or slot id outside the batch");
+        return MAPF_ESTATE;
+    }
     if (bits & MAPF_ERRBIT_ACTION) {
         mapf_set_error("action index out of range");
         return MAPF_EACTION;
@@ -790,6 +857,10 @@ int mapf_env_status(mapf_env *env, void *stream)
     if (bits & MAPF_ERRBIT_RESET) {
         mapf_set_error("no empty position");  // environment.py:31
         return MAPF_ENOSPACE;
+    }
+    if (bits & MAPF_ERRBIT_INTERNAL) {
+        mapf_set_error("rollout scheduler: a chunk hand-over never arrived");
+        return MAPF_EINTERNAL;
     }
     return MAPF_OK;
 }
@@ -838,8 +909,10 @@ int mapf_per_create(int64_t capacity, int32_t device, mapf_per **out)
     if (rc == MAPF_OK) rc = dev_alloc(&t->scratch.stamps, (size_t)capacity, &total);
     if (rc == MAPF_OK) rc = dev_alloc(&t->scratch.prio32, (size_t)t->scratch.cap_n, &total);
     if (rc == MAPF_OK) rc = dev_alloc(&t->scratch.active, (size_t)t->scratch.cap_n, &total);
+    if (rc == MAPF_OK) rc = dev_alloc(&t->scratch.err, 1, &total);
     if (rc == MAPF_OK) {
         cudaError_t e = cudaMemset(t->tree, 0, (size_t)nodes * 8);
+        if (e == cudaSuccess) e = cudaMemset(t->scratch.err, 0, 4);
         if (e == cudaSuccess) e = cudaMemset(t->scratch.stamps, 0, (size_t)capacity * 8);
         if (e == cudaSuccess) e = cudaDeviceSynchronize();
         if (e != cudaSuccess) rc = mapf_cuda_fail(e, "cudaMemset(tree)");
@@ -860,6 +933,7 @@ int mapf_per_destroy(mapf_per *t)
     cudaFree(t->scratch.stamps);
     cudaFree(t->scratch.prio32);
     cudaFree(t->scratch.active);
+    cudaFree(t->scratch.err);
     delete t;
     return MAPF_OK;
 }
@@ -915,14 +989,56 @@ int mapf_per_td_update(mapf_per *t, const float *d_q_online, const float *d_q_ta
                                      static_cast<cudaStream_t>(stream));
 }
 
+int mapf_per_cycle(mapf_per *t, const mapf_per_cycle_args *a, void *stream)
+{
+    REQUIRE_PER(t);
+    if (!a || a->n_update < 0 || a->n_sample < 0 || a->n_update > t->scratch.cap_n) {
+        mapf_set_error("mapf_per_cycle: bad arguments (n_update <= 65536)");
+        return MAPF_EINVAL;
+    }
+    if (a->n_update > 0 && (!a->d_q_online || !a->d_q_target_next || !a->d_action || !a->d_reward || !a->d_done || !a->d_steps || !a->d_idx)) {
+        mapf_set_error("mapf_per_cycle: NULL buffer in the update half");
+        return MAPF_EINVAL;
+    }
+    if (a->n_sample > 0 && (!a->d_uniforms || !a->d_sample_idx_out || !a->d_sample_prio_out)) {
+        mapf_set_error("mapf_per_cycle: NULL buffer in the sample half");
+        return MAPF_EINVAL;
+    }
+    return mapf_launch_per_cycle(t, &t->scratch, a, static_cast<cudaStream_t>(stream));
+}
+
+int mapf_per_status(mapf_per *t, void *stream)
+{
+    REQUIRE_PER(t);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    int32_t bits = 0;
+    MAPF_CUDA(cudaMemcpyAsync(&bits, t->scratch.err, 4, cudaMemcpyDeviceToHost, st));
+    MAPF_CUDA(cudaStreamSynchronize(st));
+    if (bits) {
+        MAPF_CUDA(cudaMemsetAsync(t->scratch.err, 0, 4, st));
+        MAPF_CUDA(cudaStreamSynchronize(st));
+        mapf_set_error("sum tree: leaf index outside [0, capacity) (skipped)");
+        return MAPF_EINDEX;
+    }
+    return MAPF_OK;
+}
+
+int mapf_actor_td_n(const float *d_rew, const float *d_q, const uint8_t *d_act, const int32_t *d_size, int32_t episodes,
+                    int32_t capacity, int32_t forward_steps, double gamma, double *d_td_out, void *stream)
+{
+    if (episodes < 0 || capacity < 1 || forward_steps < 1 || forward_steps > 8 ||
+        (episodes > 0 && (!d_rew || !d_q || !d_act || !d_size || !d_td_out))) {
+        mapf_set_error("mapf_actor_td: bad arguments (1 <= forward_steps <= 8)");
+        return MAPF_EINVAL;
+    }
+    return mapf_launch_actor_td(d_rew, d_q, d_act, d_size, episodes, capacity, forward_steps, gamma, d_td_out,
+                                static_cast<cudaStream_t>(stream));
+}
+
 int mapf_actor_td(const float *d_rew, const float *d_q, const uint8_t *d_act, const int32_t *d_size, int32_t episodes,
                   int32_t capacity, double *d_td_out, void *stream)
 {
-    if (episodes < 0 || capacity < 1 || (episodes > 0 && (!d_rew || !d_q || !d_act || !d_size || !d_td_out))) {
-        mapf_set_error("mapf_actor_td: bad arguments");
-        return MAPF_EINVAL;
-    }
-    return mapf_launch_actor_td(d_rew, d_q, d_act, d_size, episodes, capacity, d_td_out, static_cast<cudaStream_t>(stream));
+    return mapf_actor_td_n(d_rew, d_q, d_act, d_size, episodes, capacity, 2, 0.99, d_td_out, stream);  // config.py:30, buffer.py:175
 }
 
 int mapf_replay_gather(const mapf_replay_view *view, const int64_t *d_idx, int64_t batch, const mapf_replay_batch *out,

@@ -56,43 +56,89 @@ struct mapf_env {
     cudaEvent_t chain_fork;
     // long rollouts replay, per chain, a captured graph of one slot period (P = lcm of the slot counts) of launches
     struct RolloutGraph {
-        const void *act, *obs, *rew, *done, *steps;
+        const void *act, *obs, *rew, *codes, *done, *steps;
         int action_slots, obs_slots, out_slots, S, P, tuning_gen;
         cudaGraphExec_t exec[MAPF_MAX_CHAINS];
     } rg[2];
     int rg_next;
-    int split_key, split_per_sm;  // resident CTAs per SM of the split step kernel, cached per (variant) key
-    // staging for the host-buffer entry point
+    // persistent rollout kernel (mapf_rollout_kernels.cu): scheduler words, resident CTAs per SM (cached per store mode)
+    unsigned long long *ro_work;  // [0] next work item, [1] warps that have left; both 0 between launches
+    uint32_t *ro_progress;        // [B] chunks of an environment finished inside the running launch
+    uint32_t *ro_episode;         // [B] instances generated for the slot by in-launch episode handling
+    int ro_key, ro_per_sm;
+    // episode handling inside mapf_env_rollout (mapf_env_set_autoreset); ar_max_steps == 0: off
+    int ar_max_steps;
+    unsigned long long ar_seed, ar_offset, ar_stride;
+    float ar_density;
+    int check_unique;             // post-step uniqueness check (environment.py:424-428) in every step launch
+    // staging for the host-buffer entry points
     uint8_t *d_actions;
     uint8_t *d_obs;
     float *d_rewards;
     uint8_t *d_done;
     int32_t *d_steps_out;
-    uint8_t *h_pinned;  // pinned staging: actions | rewards | done | steps
-    // last caller buffers of mapf_env_step_host and what they resolved to (a per-step actor reuses its buffers, so
-    // the four cudaPointerGetAttributes / cudaHostGetDevicePointer queries are paid once)
-    uint8_t *pin_alias;  // device alias of h_pinned
+    uint8_t *h_pinned;  // pinned staging: actions | rewards or codes | steps | done
     cudaStream_t side_stream;          // result copies of mapf_env_step_host run here, next to the observe kernel
     cudaEvent_t ev_stepped, ev_copied;
     // the same sequence captured once per (buffer set, observation target) and replayed with one launch
     struct HostGraph {
         const void *act, *rew, *done, *steps, *hobs, *obs_dev;
-        int mode;
+        int gen;
         cudaGraphExec_t exec;
     } hg[32];
     int hg_next;
+    int checks_gen;
     cudaStream_t cap_stream;
-    struct PtrInfo {
-        const void *key;
-        bool pinned;
-        void *alias;
-    } ptr_cache[32];
-    int ptr_cache_next;
-    const void *hc_key[4];
-    void *hc_alias[4];   // device alias of the page-locked buffer, or NULL
-    bool hc_pinned[4];
+    // mapf_env_step_host_codes: completion flag in page-locked host memory (and its device alias), publication counter
+    volatile uint32_t *h_flag;
+    uint32_t *d_flag;
+    uint32_t *pub_counter;
+    uint32_t pub_seq;
     int64_t arena_bytes;
 };
+
+struct StepParams {
+    EnvDims d;
+    const uint32_t *obst;
+    uint8_t *pos;
+    const uint8_t *goal;
+    const uint32_t *navi;
+    int32_t *steps;
+    int32_t *err;
+    const uint8_t *actions;  // [B,N]           (step only)
+    uint8_t *obs;            // [B,N,6,9,9], or the base of a replay store when obs_rows is given
+    const int64_t *obs_rows; // optional [B]: env e writes its N*486-byte block at row obs_rows[e] of `obs`
+    float *rewards;          // [B,N] optional  (step only)
+    uint8_t *codes;          // [B,N] optional  (step only): index of the reward in reward_fn order (MAPF_RCODE_*)
+    uint8_t *done;           // [B]             (step only)
+    int32_t *steps_out;      // [B] optional
+    uint8_t *pos_out;        // [B,N,2] optional (observe only)
+    float r[5];              // reward_fn in MAPF_RCODE order: move, stay_on_goal, stay_off_goal, collision, finish
+    int warp_smem_words;     // per-warp shared memory, multiple of 4 words
+    int obst_words;          // = d.obst_stride
+    int bits_words;          // words of the per-env observation bit stream (also holds the occupancy grid)
+    int flags;               // MAPF_STEPF_*
+    int env_begin, env_end;  // the launch covers environments [env_begin, env_end) of the batch
+};
+
+// optional host publication of a step's results (see step_observe_kernel)
+struct StepPublish {
+    uint32_t *counter = nullptr;  // device: environments of the launch that have published
+    uint32_t *flag = nullptr;     // device alias of a page-locked host word: receives `seq` once every environment has published
+    uint32_t seq = 0;
+};
+
+// outputs of a step launch; rewards and codes are each optional
+struct StepOut {
+    float *rewards = nullptr;   // f32[B,N]
+    uint8_t *codes = nullptr;   // u8[B,N] MAPF_RCODE_*
+    uint8_t *done = nullptr;    // u8[B]
+    int32_t *steps = nullptr;   // i32[B] optional
+    StepPublish pub;
+};
+
+struct mapf_env;
+StepParams mapf_make_step_params(const mapf_env *env);
 
 // scratch owned by a tree handle
 struct PerScratch {
@@ -101,6 +147,7 @@ struct PerScratch {
     uint8_t *active;             // u8[cap_n]
     int64_t cap_n;
     unsigned long long epoch;
+    int32_t *err;                // latched device error bits (MAPF_ERRBIT_INDEX)
 };
 
 struct mapf_per {
@@ -123,3 +170,6 @@ int mapf_cuda_fail(cudaError_t e, const char *what);
 #define MAPF_ERRBIT_ACTION 1
 #define MAPF_ERRBIT_UNIQUE 2
 #define MAPF_ERRBIT_RESET 4
+#define MAPF_ERRBIT_INTERNAL 8   /* rollout scheduler: a chunk hand-over never arrived */
+#define MAPF_ERRBIT_STATE 16     /* load / set_state: coordinate outside the map, start on an obstacle, duplicate start, bad slot id */
+#define MAPF_ERRBIT_INDEX 32     /* sum tree: leaf index outside [0, capacity) */

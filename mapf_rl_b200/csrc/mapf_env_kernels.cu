@@ -9,6 +9,7 @@
 // observation bytes (486 B per agent-step); everything else stays in shared memory / registers.
 #include <type_traits>
 
+#include "mapf_bfs_device.cuh"
 #include "mapf_common.cuh"
 
 namespace {
@@ -23,11 +24,15 @@ __device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
 __global__ void pack_load_kernel(EnvDims d, const int32_t *__restrict__ env_ids, int n, const uint8_t *__restrict__ maps,
                                  const uint8_t *__restrict__ agents, const uint8_t *__restrict__ goals,
                                  uint32_t *__restrict__ obst, uint8_t *__restrict__ pos, uint8_t *__restrict__ goal,
-                                 int32_t *__restrict__ steps)
+                                 int32_t *__restrict__ steps, int32_t *__restrict__ err)
 {
     int i = blockIdx.x;
     if (i >= n) return;
     int e = env_ids ? env_ids[i] : i;
+    if (e < 0 || e >= d.B) {  // a slot id outside the batch: nothing is written (the reference would raise IndexError)
+        if (threadIdx.x == 0) atomicOr(err, MAPF_ERRBIT_STATE);
+        return;
+    }
     const uint8_t *m = maps + (size_t)i * d.L * d.L;
     uint32_t *o = obst + (size_t)e * d.obst_stride;
     for (int w = threadIdx.x; w < d.obst_stride; w += blockDim.x) {
@@ -50,19 +55,53 @@ __global__ void pack_load_kernel(EnvDims d, const int32_t *__restrict__ env_ids,
 }
 
 // ---------------------------------------------------------------------------------------------
-// K3: bit-parallel wavefront BFS                                   (environment.py:217-276)
-//
-// Lane l owns the RPL consecutive map rows RPL*l .. RPL*l + RPL - 1 (blocked, so that only the first and
-// the last of them need a neighbour lane: two shuffles per word and wave whatever RPL is), each row RW words
-// of padded column bits.  One wave:
-//   new = (frontier shifted to the four neighbours) & free-and-unvisited
-// and the heuristic bit "neighbour in direction d is strictly closer" (environment.py:260-274) is
-// exactly "this cell is new in wave t and that neighbour was in the frontier of wave t-1", so the
-// four direction planes fall out of the same step and no distance array is needed.
+// state validation after load / set_state: the step kernel indexes shared memory with the coordinates, so a coordinate
+// outside the map must never reach it.  Out-of-range coordinates are clamped into the map and latched as
+// MAPF_ERRBIT_STATE (the reference raises IndexError on the same input); two agents on one cell are latched as
+// MAPF_ERRBIT_UNIQUE (the reference raises RuntimeError('unique') at the next step, environment.py:424-428).
+// One warp per environment.
 // ---------------------------------------------------------------------------------------------
-// APW agents share a warp (LW = 32 / APW lanes each): maps of up to 48 rows fit 16 lanes x 3 rows, so two agents' waves
-// run in one instruction stream (at 40x40 one agent per warp leaves 12 of 32 lanes idle); the warp iterates until
-// both are done.
+__global__ void validate_state_kernel(EnvDims d, const int32_t *__restrict__ env_ids, int n, uint8_t *__restrict__ pos,
+                                      uint8_t *__restrict__ goal, int32_t *__restrict__ err)
+{
+    const int i = blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (i >= n) return;
+    const int lane = threadIdx.x & 31;
+    const int e = env_ids ? env_ids[i] : i;
+    if (e < 0 || e >= d.B) return;  // latched by pack_load_kernel
+    uchar2 *pp = reinterpret_cast<uchar2 *>(pos) + (size_t)e * d.N;
+    uchar2 *gg = reinterpret_cast<uchar2 *>(goal) + (size_t)e * d.N;
+    bool bad = false;
+    for (int a = lane; a < d.N; a += 32) {
+        uchar2 p = pp[a], g = gg[a];
+        if (p.x >= d.L || p.y >= d.L) {
+            bad = true;
+            p.x = min((int)p.x, d.L - 1), p.y = min((int)p.y, d.L - 1);
+            pp[a] = p;
+        }
+        if (g.x >= d.L || g.y >= d.L) {
+            bad = true;
+            g.x = min((int)g.x, d.L - 1), g.y = min((int)g.y, d.L - 1);
+            gg[a] = g;
+        }
+    }
+    __syncwarp();
+    bool dup = false;
+    for (int a = lane; a < d.N; a += 32) {
+        const uchar2 p = pp[a];
+        for (int b = 0; b < a; ++b) {
+            const uchar2 q = pp[b];
+            if (q.x == p.x && q.y == p.y) dup = true;
+        }
+    }
+    bad = __any_sync(MAPF_FULL_MASK, bad);
+    dup = __any_sync(MAPF_FULL_MASK, dup);
+    if (lane == 0 && (bad || dup)) atomicOr(err, (bad ? MAPF_ERRBIT_STATE : 0) | (dup ? MAPF_ERRBIT_UNIQUE : 0));
+}
+
+// ---------------------------------------------------------------------------------------------
+// K3: bit-parallel wavefront BFS (environment.py:217-276): one warp per APW agents, see mapf_bfs_device.cuh
+// ---------------------------------------------------------------------------------------------
 template <int RW, int RPL, int APW>
 __global__ void __launch_bounds__(kBfsWarps * 32, RW * RPL <= 9 ? 8 : 1)  // <= 64 registers (32 resident warps per SM)
                                                                           // wherever that does not spill
@@ -71,180 +110,14 @@ bfs_navi_kernel(EnvDims d, const int32_t *__restrict__ env_ids, const uint8_t *_
                 int32_t *__restrict__ dist_out)
 {
     constexpr int LW = 32 / APW;
-    const int lane = lane_id() % LW;             // lane within the agent's group
     const int g = (blockIdx.x * kBfsWarps + (threadIdx.x >> 5)) * APW + lane_id() / LW;
     bool alive = g < n * d.N;
     const int i = alive ? g / d.N : 0, a = alive ? g - i * d.N : 0;
-    const int e = env_ids ? env_ids[i] : i;
+    int e = env_ids ? env_ids[i] : i;
+    if (e < 0 || e >= d.B) alive = false, e = 0;           // bad slot id: latched by pack_load_kernel
     if (alive && env_mask && !env_mask[e]) alive = false;  // masked re-computation after a device-side reset
     if (!__any_sync(MAPF_FULL_MASK, alive)) return;
-    const uint32_t *ob = obst + (size_t)e * d.obst_stride;
-
-    // unv = free and not yet visited, fro = frontier of the previous wave, pl = the four heuristic planes
-    uint32_t unv[RPL][RW], fro[RPL][RW], pl[4][RPL][RW];
-    const int gx = goal[((size_t)e * d.N + a) * 2], gy = goal[((size_t)e * d.N + a) * 2 + 1];
-#pragma unroll
-    for (int q = 0; q < RPL; ++q) {
-        const int row = alive ? lane * RPL + q : d.L;  // a group without an agent owns no rows
-#pragma unroll
-        for (int w = 0; w < RW; ++w) {
-            // in-map column mask for this word: padded bits [4, L+4)
-            int lo = max(4 - 32 * w, 0), hi = min(d.L + 4 - 32 * w, 32);
-            uint32_t cm = 0;
-            if (hi > lo) cm = (hi - lo == 32) ? 0xffffffffu : (((1u << (hi - lo)) - 1u) << lo);
-            const uint32_t fre = (row < d.L) ? (~__ldg(ob + (row + 4) * d.RWS + w) & cm) : 0u;
-            const int p = gy + 4;
-            fro[q][w] = (row == gx && (p >> 5) == w) ? ((1u << (p & 31)) & fre) : 0u;
-            unv[q][w] = fre & ~fro[q][w];
-#pragma unroll
-            for (int k = 0; k < 4; ++k) pl[k][q][w] = 0;
-        }
-    }
-
-    int32_t *dist = (dist_out && alive) ? dist_out + ((size_t)i * d.N + a) * d.L * d.L : nullptr;
-    if (dist_out) {
-        for (int q = 0; q < RPL; ++q) {
-            const int row = lane * RPL + q;
-            if (dist && row < d.L)
-                for (int y = 0; y < d.L; ++y) dist[row * d.L + y] = MAPF_DIST_UNREACHABLE;
-        }
-        __syncwarp();
-#pragma unroll
-        for (int q = 0; q < RPL; ++q)
-#pragma unroll
-            for (int w = 0; w < RW; ++w)
-                if (dist && fro[q][w]) dist[gx * d.L + gy] = 0;
-    }
-
-    // Wavefront loop.  Adjacent reachable cells of a 4-connected grid differ by exactly one in distance, so "the
-    // neighbour is strictly closer" (environment.py:260-274) is "its distance mod 3 is mine minus one": the loop only
-    // records WHICH residue a cell's wave had (m1 / m2; residue 0 = reached and in neither) -- one LOP per word and wave
-    // instead of four plane updates -- and the four planes are derived once at the end.
-    uint32_t m1[RPL][RW], m2[RPL][RW];
-#pragma unroll
-    for (int q = 0; q < RPL; ++q)
-#pragma unroll
-        for (int w = 0; w < RW; ++w) m1[q][w] = m2[q][w] = 0;
-    auto wave = [&](auto selc, const int t) -> bool {
-        constexpr int sel = decltype(selc)::value;  // t mod 3
-        uint32_t nw[RPL][RW];
-        uint32_t any = 0;
-#pragma unroll
-        for (int w = 0; w < RW; ++w) {
-            // rows of the neighbouring lanes that touch this lane's block
-            uint32_t above = __shfl_up_sync(MAPF_FULL_MASK, fro[RPL - 1][w], 1, LW);
-            uint32_t below = __shfl_down_sync(MAPF_FULL_MASK, fro[0][w], 1, LW);
-            if (lane == 0) above = 0;
-            if (lane == LW - 1) below = 0;
-#pragma unroll
-            for (int q = 0; q < RPL; ++q) {
-                const uint32_t f = fro[q][w];
-                const uint32_t fl = w > 0 ? __funnelshift_l(fro[q][w > 0 ? w - 1 : 0], f, 1) : f << 1;
-                const uint32_t fr = w < RW - 1 ? __funnelshift_r(f, fro[q][w < RW - 1 ? w + 1 : w], 1) : f >> 1;
-                const uint32_t up = q > 0 ? fro[q > 0 ? q - 1 : 0][w] : above;
-                const uint32_t dn = q < RPL - 1 ? fro[q < RPL - 1 ? q + 1 : q][w] : below;
-                const uint32_t x = (fl | fr | up | dn) & unv[q][w];
-                nw[q][w] = x;
-                any |= x;
-            }
-        }
-        if (!__any_sync(MAPF_FULL_MASK, any != 0)) return false;
-#pragma unroll
-        for (int q = 0; q < RPL; ++q)
-#pragma unroll
-            for (int w = 0; w < RW; ++w) {
-                unv[q][w] &= ~nw[q][w];
-                fro[q][w] = nw[q][w];
-                if constexpr (sel == 1) m1[q][w] |= nw[q][w];
-                if constexpr (sel == 2) m2[q][w] |= nw[q][w];
-                if (dist_out) {  // a kernel argument: the loop is compiled twice, the common one without any of this
-                    uint32_t x = dist ? nw[q][w] : 0u;
-                    while (x) {
-                        int b = __ffs(x) - 1;
-                        x &= x - 1;
-                        dist[(lane * RPL + q) * d.L + (32 * w + b - 4)] = t;
-                    }
-                }
-            }
-        return true;
-    };
-    for (int t = 1;; t += 3) {
-        if (!wave(std::integral_constant<int, 1>{}, t)) break;
-        if (!wave(std::integral_constant<int, 2>{}, t + 1)) break;
-        if (!wave(std::integral_constant<int, 0>{}, t + 2)) break;
-    }
-
-    // The four heuristic planes from the residues: with z = reached cells of residue 0, direction "neighbour n is
-    // closer" holds at a cell c iff (c in m1, n in z) or (c in m2, n in m1) or (c in z, n in m2).
-    {
-        uint32_t z[RPL][RW];
-#pragma unroll
-        for (int q = 0; q < RPL; ++q) {
-            const int row = alive ? lane * RPL + q : d.L;
-#pragma unroll
-            for (int w = 0; w < RW; ++w) {
-                int lo = max(4 - 32 * w, 0), hi = min(d.L + 4 - 32 * w, 32);
-                uint32_t cm = 0;
-                if (hi > lo) cm = (hi - lo == 32) ? 0xffffffffu : (((1u << (hi - lo)) - 1u) << lo);
-                const uint32_t fre = (row < d.L) ? (~__ldg(ob + (row + 4) * d.RWS + w) & cm) : 0u;
-                z[q][w] = fre & ~unv[q][w] & ~m1[q][w] & ~m2[q][w];
-            }
-        }
-        auto closer = [](uint32_t c1, uint32_t c2, uint32_t cz, uint32_t n1, uint32_t n2, uint32_t nz) -> uint32_t {
-            return (c1 & nz) | (c2 & n1) | (cz & n2);
-        };
-#pragma unroll
-        for (int w = 0; w < RW; ++w) {
-            // residue rows of the neighbouring lanes that touch this lane's block
-            uint32_t a1 = __shfl_up_sync(MAPF_FULL_MASK, m1[RPL - 1][w], 1, LW), b1 = __shfl_down_sync(MAPF_FULL_MASK, m1[0][w], 1, LW);
-            uint32_t a2 = __shfl_up_sync(MAPF_FULL_MASK, m2[RPL - 1][w], 1, LW), b2 = __shfl_down_sync(MAPF_FULL_MASK, m2[0][w], 1, LW);
-            uint32_t az = __shfl_up_sync(MAPF_FULL_MASK, z[RPL - 1][w], 1, LW), bz = __shfl_down_sync(MAPF_FULL_MASK, z[0][w], 1, LW);
-            if (lane == 0) a1 = a2 = az = 0;
-            if (lane == LW - 1) b1 = b2 = bz = 0;
-#pragma unroll
-            for (int q = 0; q < RPL; ++q) {
-                auto left = [&](const uint32_t(&m)[RPL][RW]) {  // bit y <- bit y-1
-                    return w > 0 ? __funnelshift_l(m[q][w > 0 ? w - 1 : 0], m[q][w], 1) : m[q][w] << 1;
-                };
-                auto right = [&](const uint32_t(&m)[RPL][RW]) {  // bit y <- bit y+1
-                    return w < RW - 1 ? __funnelshift_r(m[q][w], m[q][w < RW - 1 ? w + 1 : w], 1) : m[q][w] >> 1;
-                };
-                const uint32_t c1 = m1[q][w], c2 = m2[q][w], cz = z[q][w];
-                const uint32_t u1 = q > 0 ? m1[q > 0 ? q - 1 : 0][w] : a1, u2 = q > 0 ? m2[q > 0 ? q - 1 : 0][w] : a2,
-                               uz = q > 0 ? z[q > 0 ? q - 1 : 0][w] : az;
-                const uint32_t d1 = q < RPL - 1 ? m1[q < RPL - 1 ? q + 1 : q][w] : b1, d2 = q < RPL - 1 ? m2[q < RPL - 1 ? q + 1 : q][w] : b2,
-                               dz = q < RPL - 1 ? z[q < RPL - 1 ? q + 1 : q][w] : bz;
-                pl[0][q][w] = closer(c1, c2, cz, u1, u2, uz);                       // neighbour x-1   environment.py:260
-                pl[1][q][w] = closer(c1, c2, cz, d1, d2, dz);                       // neighbour x+1   environment.py:264
-                pl[2][q][w] = closer(c1, c2, cz, left(m1), left(m2), left(z));      // neighbour y-1   environment.py:268
-                pl[3][q][w] = closer(c1, c2, cz, right(m1), right(m2), right(z));   // neighbour y+1   environment.py:272
-            }
-        }
-    }
-
-    // emit the overlapping 16x16 tiles (mapf_common.cuh): a map row is padded row pr = row + 4, which is
-    // row pr & 7 of tile row-block pr >> 3 and row (pr & 7) + 8 of the block above
-    uint2 *nv = reinterpret_cast<uint2 *>(navi + ((size_t)e * d.N + a) * d.navi_agent_stride);
-#pragma unroll
-    for (int q = 0; q < RPL; ++q) {
-        const int row = lane * RPL + q;
-        if (row >= d.L || !alive) continue;
-        const int pr = row + 4, bx1 = pr >> 3, r1 = pr & 7;
-#pragma unroll
-        for (int by = 0; by < 4 * RW; ++by) {
-            if (by >= d.NB) continue;
-            constexpr int kLast = RW - 1;
-            const int w = by >> 2;          // compile-time after unrolling
-            const int s = (by & 3) * 8;
-            uint32_t f[4];
-#pragma unroll
-            for (int k = 0; k < 4; ++k)
-                f[k] = __funnelshift_r(pl[k][q][w], w < kLast ? pl[k][q][w < kLast ? w + 1 : kLast] : 0u, s) & 0xffffu;
-            const uint2 v = make_uint2(f[0] | (f[1] << 16), f[2] | (f[3] << 16));
-            if (bx1 < d.NB) nv[((size_t)(bx1 * d.NB + by) << 4) + r1] = v;
-            if (bx1 > 0) nv[((size_t)((bx1 - 1) * d.NB + by) << 4) + r1 + 8] = v;
-        }
-    }
+    bfs_navi_warp<RW, RPL, APW>(d, e, a, i, alive, obst, goal, navi, dist_out);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -343,7 +216,16 @@ int mapf_launch_pack_load(mapf_env *env, const int32_t *d_env_ids, int n, const 
                           const uint8_t *d_agents, const uint8_t *d_goals, cudaStream_t st)
 {
     pack_load_kernel<<<n, 128, 0, st>>>(env->d, d_env_ids, n, d_maps, d_agents, d_goals, env->obst, env->pos, env->goal,
-                                        env->steps);
+                                        env->steps, env->err);
+    MAPF_CUDA(cudaGetLastError());
+    return MAPF_OK;
+}
+
+// slots env_ids[0..n) (NULL: slots 0..n-1)
+int mapf_launch_validate_state(mapf_env *env, const int32_t *d_env_ids, int n, cudaStream_t st)
+{
+    if (n <= 0) return MAPF_OK;
+    validate_state_kernel<<<(n + 3) / 4, 128, 0, st>>>(env->d, d_env_ids, n, env->pos, env->goal, env->err);
     MAPF_CUDA(cudaGetLastError());
     return MAPF_OK;
 }

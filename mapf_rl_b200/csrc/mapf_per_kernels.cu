@@ -8,6 +8,8 @@
 // disabled.  The whole tree (8 MiB at the reference's 2^19 leaves) lives in L2; the kernels are
 // latency-bound (layer-1 dependent levels), not bandwidth-bound, so one CTA handles a batch and the
 // fused learner tail (TD -> priority -> leaf write -> ancestor refresh) is a single launch.
+#include <cmath>
+
 #include "mapf_common.cuh"
 
 namespace {
@@ -20,18 +22,26 @@ __device__ __forceinline__ unsigned long long stamp_of(unsigned long long epoch,
 }
 
 // Leaf writes with numpy's duplicate rule, then the level-by-level ancestor refresh.  Single CTA.
-// `active[k]` (optional) masks entries out (stale indices, worker.py:192-201).
+// `active[k]` (optional) masks entries out (stale indices, worker.py:192-201).  An index outside [0, capacity) -- numpy
+// raises IndexError -- is skipped and latched in *err (mapf_per_status).
 __device__ void tree_update_cta(double *tree, unsigned long long *stamps, unsigned long long epoch, int64_t capacity,
                                 int layer, const int64_t *idx, const double *prio_in, const float *prio32, double alpha,
-                                const uint8_t *active, int64_t n)
+                                const uint8_t *active, int64_t n, int32_t *err)
 {
+    auto live = [&](int64_t k) -> bool {
+        if (active && !active[k]) return false;
+        const int64_t i = idx[k];
+        return i >= 0 && i < capacity;
+    };
     // phase 1: the highest batch position claims each leaf
-    for (int64_t k = threadIdx.x; k < n; k += blockDim.x)
-        if (!active || active[k]) atomicMax(&stamps[idx[k]], stamp_of(epoch, k));
+    for (int64_t k = threadIdx.x; k < n; k += blockDim.x) {
+        if (live(k)) atomicMax(&stamps[idx[k]], stamp_of(epoch, k));
+        else if (!active || active[k]) atomicOr(err, MAPF_ERRBIT_INDEX);
+    }
     __syncthreads();
     // phase 2: winners store the leaf
     for (int64_t k = threadIdx.x; k < n; k += blockDim.x) {
-        if (active && !active[k]) continue;
+        if (!live(k)) continue;
         if (stamps[idx[k]] == stamp_of(epoch, k)) {
             double v = prio_in ? prio_in[k] : pow((double)prio32[k], alpha);
             tree[capacity - 1 + idx[k]] = v;
@@ -42,7 +52,7 @@ __device__ void tree_update_cta(double *tree, unsigned long long *stamps, unsign
     // twice from final children gives the same bits)
     for (int l = 1; l < layer; ++l) {
         for (int64_t k = threadIdx.x; k < n; k += blockDim.x) {
-            if (active && !active[k]) continue;
+            if (!live(k)) continue;
             int64_t node = ((capacity - 1 + idx[k] + 1) >> l) - 1;  // l-th ancestor in the array heap
             tree[node] = __dadd_rn(tree[2 * node + 1], tree[2 * node + 2]);
         }
@@ -52,37 +62,39 @@ __device__ void tree_update_cta(double *tree, unsigned long long *stamps, unsign
 
 __global__ void __launch_bounds__(kPerThreads)
 per_update_kernel(double *tree, unsigned long long *stamps, unsigned long long epoch, int64_t capacity, int layer,
-                  const int64_t *idx, const double *prio, int64_t n)
+                  const int64_t *idx, const double *prio, int64_t n, int32_t *err)
 {
-    tree_update_cta(tree, stamps, epoch, capacity, layer, idx, prio, nullptr, 0.0, nullptr, n);
+    tree_update_cta(tree, stamps, epoch, capacity, layer, idx, prio, nullptr, 0.0, nullptr, n, err);
 }
 
 // multi-CTA variants for batches larger than one CTA handles comfortably
-__global__ void per_claim_kernel(unsigned long long *stamps, unsigned long long epoch, const int64_t *idx, int64_t n)
+__global__ void per_claim_kernel(unsigned long long *stamps, unsigned long long epoch, int64_t capacity, const int64_t *idx, int64_t n,
+                                 int32_t *err)
 {
     int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (k < n) atomicMax(&stamps[idx[k]], stamp_of(epoch, k));
+    if (k >= n) return;
+    if (idx[k] >= 0 && idx[k] < capacity) atomicMax(&stamps[idx[k]], stamp_of(epoch, k));
+    else atomicOr(err, MAPF_ERRBIT_INDEX);
 }
 __global__ void per_leaf_kernel(double *tree, const unsigned long long *stamps, unsigned long long epoch, int64_t capacity,
                                 const int64_t *idx, const double *prio, int64_t n)
 {
     int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (k < n && stamps[idx[k]] == stamp_of(epoch, k)) tree[capacity - 1 + idx[k]] = prio[k];
+    if (k < n && idx[k] >= 0 && idx[k] < capacity && stamps[idx[k]] == stamp_of(epoch, k)) tree[capacity - 1 + idx[k]] = prio[k];
 }
 __global__ void per_level_kernel(double *tree, int64_t capacity, int l, const int64_t *idx, int64_t n)
 {
     int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (k < n) {
+    if (k < n && idx[k] >= 0 && idx[k] < capacity) {
         int64_t node = ((capacity - 1 + idx[k] + 1) >> l) - 1;
         tree[node] = __dadd_rn(tree[2 * node + 1], tree[2 * node + 2]);
     }
 }
 
 // SumTree.batch_sample, buffer.py:56-78.  One thread per sample, layer-1 dependent L2 reads.
-__global__ void __launch_bounds__(kPerThreads)
-per_sample_kernel(const double *__restrict__ tree, int64_t capacity, int layer, const double *__restrict__ uniforms,
-                  int64_t batch, int64_t *__restrict__ idx_out, double *__restrict__ prio_out,
-                  float *__restrict__ weight_out, double beta)
+__device__ void sample_cta(const double *__restrict__ tree, int64_t capacity, int layer, const double *__restrict__ uniforms,
+                           int64_t batch, int64_t *__restrict__ idx_out, double *__restrict__ prio_out,
+                           float *__restrict__ weight_out, double beta)
 {
     __shared__ double s_min[32];
     const double sum = tree[0];
@@ -118,15 +130,21 @@ per_sample_kernel(const double *__restrict__ tree, int64_t capacity, int layer, 
     }
 }
 
-// Fused learner tail: TD error -> priority -> stale mask -> leaf = prio^alpha -> ancestor refresh.
 __global__ void __launch_bounds__(kPerThreads)
-per_td_update_kernel(double *tree, unsigned long long *stamps, unsigned long long epoch, int64_t capacity, int layer,
-                     const float *__restrict__ q_online, const float *__restrict__ q_target_next,
-                     const float *__restrict__ q_online_next, const int64_t *__restrict__ action,
-                     const float *__restrict__ reward, const float *__restrict__ done, const float *__restrict__ steps,
-                     const int64_t *__restrict__ idx, int64_t n, float gamma, double alpha, int64_t old_ptr, int64_t ptr,
-                     int64_t slot_steps, float *__restrict__ td_out, float *__restrict__ prio_out, float *prio_scratch,
-                     uint8_t *active)
+per_sample_kernel(const double *__restrict__ tree, int64_t capacity, int layer, const double *__restrict__ uniforms,
+                  int64_t batch, int64_t *__restrict__ idx_out, double *__restrict__ prio_out,
+                  float *__restrict__ weight_out, double beta)
+{
+    sample_cta(tree, capacity, layer, uniforms, batch, idx_out, prio_out, weight_out, beta);
+}
+
+// Learner TD error -> priority -> stale mask (worker.py:300-308, 192-201), one thread per transition
+__device__ void td_cta(const float *__restrict__ q_online, const float *__restrict__ q_target_next,
+                       const float *__restrict__ q_online_next, const int64_t *__restrict__ action,
+                       const float *__restrict__ reward, const float *__restrict__ done, const float *__restrict__ steps,
+                       const int64_t *__restrict__ idx, int64_t n, float gamma, int64_t old_ptr, int64_t ptr,
+                       int64_t slot_steps, float *__restrict__ td_out, float *__restrict__ prio_out, float *prio_scratch,
+                       uint8_t *active)
 {
     for (int64_t k = threadIdx.x; k < n; k += blockDim.x) {
         const float *qt = q_target_next + k * 5;
@@ -157,12 +175,49 @@ per_td_update_kernel(double *tree, unsigned long long *stamps, unsigned long lon
         active[k] = keep ? 1 : 0;
     }
     __syncthreads();
-    tree_update_cta(tree, stamps, epoch, capacity, layer, idx, nullptr, prio_scratch, alpha, active, n);
 }
 
-// LocalBuffer.finish, buffer.py:170-177
+// Fused learner tail: TD error -> priority -> stale mask -> leaf = prio^alpha -> ancestor refresh.
+__global__ void __launch_bounds__(kPerThreads)
+per_td_update_kernel(double *tree, unsigned long long *stamps, unsigned long long epoch, int64_t capacity, int layer,
+                     const float *__restrict__ q_online, const float *__restrict__ q_target_next,
+                     const float *__restrict__ q_online_next, const int64_t *__restrict__ action,
+                     const float *__restrict__ reward, const float *__restrict__ done, const float *__restrict__ steps,
+                     const int64_t *__restrict__ idx, int64_t n, float gamma, double alpha, int64_t old_ptr, int64_t ptr,
+                     int64_t slot_steps, float *__restrict__ td_out, float *__restrict__ prio_out, float *prio_scratch,
+                     uint8_t *active, int32_t *err)
+{
+    td_cta(q_online, q_target_next, q_online_next, action, reward, done, steps, idx, n, gamma, old_ptr, ptr, slot_steps, td_out,
+           prio_out, prio_scratch, active);
+    tree_update_cta(tree, stamps, epoch, capacity, layer, idx, nullptr, prio_scratch, alpha, active, n, err);
+}
+
+// One learner cycle in ONE launch (north star (4)): the priorities of the batch that has just been through the two Q
+// forwards go into the tree (TD -> priority -> stale mask -> leaf -> ancestors), then the NEXT batch is drawn from the
+// refreshed tree with its importance-sampling weights (worker.py:300-308, 186-203, 106-116, 165-166).  Either half may be
+// empty (n == 0).
+__global__ void __launch_bounds__(kPerThreads)
+per_cycle_kernel(double *tree, unsigned long long *stamps, unsigned long long epoch, int64_t capacity, int layer,
+                 const mapf_per_cycle_args a, float *prio_scratch, uint8_t *active, int32_t *err)
+{
+    if (a.n_update > 0) {
+        td_cta(a.d_q_online, a.d_q_target_next, a.d_q_online_next, a.d_action, a.d_reward, a.d_done, a.d_steps, a.d_idx, a.n_update,
+               a.gamma, a.old_ptr, a.ptr, a.slot_steps, a.d_td_out, a.d_prio_out, prio_scratch, active);
+        tree_update_cta(tree, stamps, epoch, capacity, layer, a.d_idx, nullptr, prio_scratch, a.alpha, active, a.n_update, err);
+    }
+    if (a.n_sample > 0)
+        sample_cta(tree, capacity, layer, a.d_uniforms, a.n_sample, a.d_sample_idx_out, a.d_sample_prio_out, a.d_sample_weight_out,
+                   a.beta);
+}
+
+// LocalBuffer.finish, buffer.py:170-177: |sum_j gamma^j r[t+j] + max_a q[t,a] - q[t,a_t]| over j < forward_steps (rewards past
+// the episode end are 0); `gpow[j]` = gamma^j as Python evaluates 0.99**j (fp64, computed on the host)
+struct ActorTdPowers {
+    double g[8];
+};
 __global__ void actor_td_kernel(const float *__restrict__ rew, const float *__restrict__ q, const uint8_t *__restrict__ act,
-                                const int32_t *__restrict__ size, int episodes, int capacity, double *__restrict__ td)
+                                const int32_t *__restrict__ size, int episodes, int capacity, int forward_steps,
+                                const ActorTdPowers gpow, double *__restrict__ td)
 {
     int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= (int64_t)episodes * capacity) return;
@@ -173,9 +228,12 @@ __global__ void actor_td_kernel(const float *__restrict__ rew, const float *__re
         const float *qq = q + g * 5;
         float qmax = qq[0];
         for (int a = 1; a < 5; ++a) qmax = fmaxf(qmax, qq[a]);
-        const double r0 = (double)rew[g];
-        const double r1 = (t + 1 < sz) ? (double)rew[g + 1] : 0.0;
-        const double conv = __dadd_rn(r0, __dmul_rn(r1, 0.99));  // np.convolve(ret, [0.99, 1.0], 'valid')
+        // np.convolve(ret, [gamma^(n-1), ..., gamma, 1.0], 'valid')[t]: accumulated from j = 0 upwards
+        double conv = __dmul_rn((double)rew[g], 1.0);
+        for (int j = 1; j < forward_steps; ++j) {
+            const double rj = (t + j < sz) ? (double)rew[g + j] : 0.0;
+            conv = __dadd_rn(conv, __dmul_rn(rj, gpow.g[j]));
+        }
         const double target = __dadd_rn(conv, (double)qmax);
         out = fabs(__dsub_rn(target, (double)qq[act[g]]));
     }
@@ -189,11 +247,11 @@ int mapf_launch_per_update(mapf_per *t, PerScratch *s, const int64_t *d_idx, con
     if (n <= 0) return MAPF_OK;
     const unsigned long long epoch = ++s->epoch;
     if (n <= 4096) {
-        per_update_kernel<<<1, kPerThreads, 0, st>>>(t->tree, s->stamps, epoch, t->capacity, t->layer, d_idx, d_prio, n);
+        per_update_kernel<<<1, kPerThreads, 0, st>>>(t->tree, s->stamps, epoch, t->capacity, t->layer, d_idx, d_prio, n, s->err);
     } else {
         const int tb = 256;
         const unsigned grid = (unsigned)((n + tb - 1) / tb);
-        per_claim_kernel<<<grid, tb, 0, st>>>(s->stamps, epoch, d_idx, n);
+        per_claim_kernel<<<grid, tb, 0, st>>>(s->stamps, epoch, t->capacity, d_idx, n, s->err);
         per_leaf_kernel<<<grid, tb, 0, st>>>(t->tree, s->stamps, epoch, t->capacity, d_idx, d_prio, n);
         for (int l = 1; l < t->layer; ++l) per_level_kernel<<<grid, tb, 0, st>>>(t->tree, t->capacity, l, d_idx, n);
     }
@@ -220,17 +278,29 @@ int mapf_launch_per_td_update(mapf_per *t, PerScratch *s, const float *q_online,
     const unsigned long long epoch = ++s->epoch;
     per_td_update_kernel<<<1, kPerThreads, 0, st>>>(t->tree, s->stamps, epoch, t->capacity, t->layer, q_online, q_target_next,
                                                     q_online_next, action, reward, done, steps, idx, n, gamma, alpha, old_ptr,
-                                                    ptr, slot_steps, td_out, prio_out, s->prio32, s->active);
+                                                    ptr, slot_steps, td_out, prio_out, s->prio32, s->active, s->err);
+    MAPF_CUDA(cudaGetLastError());
+    return MAPF_OK;
+}
+
+int mapf_launch_per_cycle(mapf_per *t, PerScratch *s, const mapf_per_cycle_args *a, cudaStream_t st)
+{
+    if (a->n_update <= 0 && a->n_sample <= 0) return MAPF_OK;
+    const unsigned long long epoch = ++s->epoch;
+    per_cycle_kernel<<<1, kPerThreads, 0, st>>>(t->tree, s->stamps, epoch, t->capacity, t->layer, *a, s->prio32, s->active, s->err);
     MAPF_CUDA(cudaGetLastError());
     return MAPF_OK;
 }
 
 int mapf_launch_actor_td(const float *d_rew, const float *d_q, const uint8_t *d_act, const int32_t *d_size, int episodes,
-                         int capacity, double *d_td_out, cudaStream_t st)
+                         int capacity, int forward_steps, double gamma, double *d_td_out, cudaStream_t st)
 {
     const int64_t total = (int64_t)episodes * capacity;
     if (total <= 0) return MAPF_OK;
-    actor_td_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(d_rew, d_q, d_act, d_size, episodes, capacity, d_td_out);
+    ActorTdPowers gp{};
+    for (int j = 0; j < 8; ++j) gp.g[j] = j == 0 ? 1.0 : (j == 1 ? gamma : std::pow(gamma, (double)j));
+    actor_td_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(d_rew, d_q, d_act, d_size, episodes, capacity, forward_steps, gp,
+                                                                     d_td_out);
     MAPF_CUDA(cudaGetLastError());
     return MAPF_OK;
 }

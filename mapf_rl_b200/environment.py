@@ -51,13 +51,15 @@ class Environment:
         if env is None:
             env = BatchedEnvironment(1, key[0], key[1], device=self._device, obs_radius=self.obs_radius,
                                      reward_fn=self.reward_fn)
+            env.set_checks(check_unique=True)   # environment.py:424-428, on the device
             self._envs[key] = env
         self._env = env
         return env
 
     def _generate(self):
-        m, a, g = generate_instance(self._rng, self.map_size[0], self.num_agents, self._fixed_density)
-        self.obstacle_density = float(m.mean())
+        m, a, g, self._last_density = generate_instance(self._rng, self.map_size[0], self.num_agents, self._fixed_density,
+                                                        return_density=True)
+        self.obstacle_density = float(self._last_density)   # the SAMPLED density, as environment.py:100,156 store it
         self._install(m, a, g)
 
     def _install(self, m, agents, goals):
@@ -65,7 +67,7 @@ class Environment:
         self.agents_pos = np.asarray(agents, dtype=np.int64).copy()
         self.goals_pos = np.asarray(goals, dtype=np.int64).copy()
         env = self._backend()
-        env.load(np.asarray(m)[None], self.agents_pos[None].astype(np.uint8), self.goals_pos[None].astype(np.uint8))
+        env.load(np.asarray(m)[None], self.agents_pos[None], self.goals_pos[None])   # range-checked, not wrapped
         self._navi_cache = None
 
     # -- reference API -------------------------------------------------------------------------
@@ -118,8 +120,7 @@ class Environment:
         table = {np.float32(v): v for v in self.reward_fn.values()}
         rewards = [table.get(r, float(r)) for r in rewards[0]]
         info = {'step': self.steps - 1}
-        if np.unique(self.agents_pos, axis=0).shape[0] < self.num_agents:  # environment.py:424-428
-            raise RuntimeError('unique')
+        self._env.check()   # environment.py:424-428: RuntimeError('unique') latched by the step kernel
         return (obs[0].astype(bool), self.agents_pos), rewards, done, info
 
     def observe(self):  # environment.py:433-467

@@ -38,8 +38,9 @@ def map_partition(map_: np.ndarray):
     return label, np.asarray(sizes, dtype=np.int64)
 
 
-def generate_instance(rng: np.random.Generator, map_length: int, num_agents: int, density=None, max_tries: int = 1000):
-    """-> (map uint8[L,L], agents int64[N,2], goals int64[N,2])"""
+def generate_instance(rng: np.random.Generator, map_length: int, num_agents: int, density=None, max_tries: int = 1000,
+                      return_density: bool = False):
+    """-> (map uint8[L,L], agents int64[N,2], goals int64[N,2]) [+ the density the map was drawn with]"""
     L, N = map_length, num_agents
     d = rng.triangular(0, 0.33, 0.5) if density is None else float(density)
     for _ in range(max_tries):
@@ -67,7 +68,7 @@ def generate_instance(rng: np.random.Generator, map_length: int, num_agents: int
             remaining[c] -= 2
             agents[i], goals[i] = s, g
         if ok:
-            return m, agents, goals
+            return (m, agents, goals, d) if return_density else (m, agents, goals)
     raise RuntimeError("no empty position")  # environment.py:31
 
 

@@ -259,6 +259,19 @@ void mo_observe(int L, int N, int r, const uint8_t *map, const int32_t *pos, con
 #ifdef _OPENMP
 #include <omp.h>
 #endif
+/* mo_navi over a batch (set-up of the batched CPU baseline): maps u8[B,L,L], goals i32[B,N,2] -> navi u8[B,N,4,L,L] */
+void mo_navi_batch(int B, int L, int N, const uint8_t *maps, const int32_t *goals, uint8_t *navi)
+{
+#ifdef _OPENMP
+#pragma omp parallel for schedule(dynamic, 8)
+#endif
+    for (int b = 0; b < B; ++b) {
+        int32_t *dist = (int32_t *)malloc(sizeof(int32_t) * (size_t)N * L * L);
+        mo_navi(L, N, maps + (size_t)b * L * L, goals + (size_t)b * N * 2, dist, navi + (size_t)b * N * 4 * L * L);
+        free(dist);
+    }
+}
+
 /* host threads used by mo_rollout (the batched CPU baseline); returns the count in effect */
 int mo_set_threads(int n)
 {
@@ -367,6 +380,27 @@ void mo_actor_td(int size, int capacity, const double *rew16, const float *q, co
         double conv = rew16[t] * 1.0 + r1 * 0.99;
         double target = conv + (double)qmax;            /* float64 + float32 -> float64 */
         td[t] = fabs(target - (double)q[t * 5 + act[t]]); /* :176-177 */
+    }
+}
+
+/* The same for config.forward_steps = n (buffer.py:174-175): ret = rew + [0]*(n-1); kernel [g^(n-1), ..., g, 1];
+ * np.convolve(ret, kernel, 'valid')[t] = sum_j ret[t+j] * g^j, accumulated from j = 0 upwards; g^j as Python's
+ * 0.99**j (pow in fp64).  n = 2, g = 0.99 is mo_actor_td. */
+void mo_actor_td_n(int size, int capacity, int n, double gamma, const double *rew16, const float *q, const uint8_t *act, double *td)
+{
+    for (int t = 0; t < capacity; ++t) td[t] = 0.0;
+    for (int t = 0; t < size; ++t) {
+        float qmax = q[t * 5];
+        for (int a = 1; a < 5; ++a)
+            if (q[t * 5 + a] > qmax) qmax = q[t * 5 + a];
+        double conv = rew16[t] * 1.0;
+        for (int j = 1; j < n; ++j) {
+            double rj = (t + j < size) ? rew16[t + j] : 0.0;
+            double gj = (j == 1) ? gamma : pow(gamma, (double)j);
+            conv = conv + rj * gj;
+        }
+        double target = conv + (double)qmax;
+        td[t] = fabs(target - (double)q[t * 5 + act[t]]);
     }
 }
 

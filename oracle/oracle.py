@@ -54,8 +54,12 @@ def lib():
         L.mo_tree_batch_sample.argtypes = [f64p, C.c_int64, C.c_int, f64p, C.c_int64, i64p, f64p]
         L.mo_actor_td.restype = None
         L.mo_actor_td.argtypes = [C.c_int, C.c_int, f64p, f32p, u8p, f64p]
+        L.mo_actor_td_n.restype = None
+        L.mo_actor_td_n.argtypes = [C.c_int, C.c_int, C.c_int, C.c_double, f64p, f32p, u8p, f64p]
         L.mo_learner_td.restype = None
         L.mo_learner_td.argtypes = [C.c_int64, f32p, f32p, i64p, f32p, f32p, f32p, f32p, f32p]
+        L.mo_navi_batch.restype = None
+        L.mo_navi_batch.argtypes = [C.c_int, C.c_int, C.c_int, u8p, i32p, u8p]
         L.mo_set_threads.restype = C.c_int
         L.mo_set_threads.argtypes = [C.c_int]
         L.mo_comm_mask.restype = None
@@ -83,6 +87,18 @@ def navi(map_: np.ndarray, goals: np.ndarray):
     nv = np.empty((N, 4, L, L), dtype=np.uint8)
     lib().mo_navi(L, N, _p(m, C.c_uint8), _p(g, C.c_int32), _p(dist, C.c_int32), _p(nv, C.c_uint8))
     return dist, nv
+
+
+def navi_batch(maps: np.ndarray, goals: np.ndarray, threads: int = 0) -> np.ndarray:
+    """maps [B,L,L], goals [B,N,2] -> navi uint8[B,N,4,L,L] (mo_navi per environment, OpenMP over the batch)."""
+    m = np.ascontiguousarray(np.asarray(maps) != 0, dtype=np.uint8)
+    g = np.ascontiguousarray(goals, dtype=np.int32)
+    B, L, N = m.shape[0], m.shape[1], g.shape[1]
+    nv = np.empty((B, N, 4, L, L), dtype=np.uint8)
+    if threads:
+        lib().mo_set_threads(int(threads))
+    lib().mo_navi_batch(B, L, N, _p(m, C.c_uint8), _p(g, C.c_int32), _p(nv, C.c_uint8))
+    return nv
 
 
 class OracleEnv:
@@ -128,26 +144,37 @@ class OracleEnv:
 
 
 def rollout(maps, pos, goals, navi_maps, actions, reward_fn=None, obs_radius=4, threads=1,
-            want_rewards=True):
+            want_rewards=True, obs_out=None, done_out=None, rewards_out=None):
     """Lockstep batch: maps u8[B,L,L], pos/goals i32[B,N,2] (pos updated in place), navi u8[B,N,4,L,L],
     actions u8[T,B,N].  Returns (rewards f32[T,B,N] | None, done u8[T,B], obs u8[B,N,6,F,F] of last step).
-    `threads` host threads share the environments (OpenMP inside mo_rollout)."""
+    `threads` host threads share the environments (OpenMP inside mo_rollout).  Caller-owned `obs_out` /
+    `done_out` / `rewards_out` of those shapes are written in place instead of allocating per call (a timed
+    loop passes them: np.zeros of the 64 MB observation block costs as much as a step of 4096 envs)."""
     B, L = maps.shape[0], maps.shape[1]
     N = pos.shape[1]
     T = actions.shape[0]
     F = 2 * obs_radius + 1
     rf = reward_vector(reward_fn)
-    rewards = np.zeros((T, B, N), dtype=np.float32) if want_rewards else None
-    done = np.zeros((T, B), dtype=np.uint8)
-    obs = np.zeros((B, N, 6, F, F), dtype=np.uint8)
+    rewards = None
+    if want_rewards:
+        rewards = rewards_out if rewards_out is not None else np.zeros((T, B, N), dtype=np.float32)
+    done = done_out if done_out is not None else np.zeros((T, B), dtype=np.uint8)
+    obs = obs_out if obs_out is not None else np.zeros((B, N, 6, F, F), dtype=np.uint8)
     assert maps.dtype == np.uint8 and pos.dtype == np.int32 and goals.dtype == np.int32
     assert navi_maps.dtype == np.uint8 and actions.dtype == np.uint8
-    for a in (maps, pos, goals, navi_maps, actions):
+    assert obs.dtype == np.uint8 and obs.shape == (B, N, 6, F, F) and done.dtype == np.uint8 and done.shape == (T, B)
+    assert rewards is None or (rewards.dtype == np.float32 and rewards.shape == (T, B, N))
+    for a in (maps, pos, goals, navi_maps, actions, obs, done):
         assert a.flags.c_contiguous
 
     def run(lo, hi):
         nb = hi - lo
         if nb <= 0:
+            return
+        if lo == 0 and hi == B:   # whole batch: every buffer is used in place
+            lib().mo_rollout(B, L, N, obs_radius, T, _p(maps, C.c_uint8), _p(pos, C.c_int32), _p(goals, C.c_int32),
+                             _p(navi_maps, C.c_uint8), _p(actions, C.c_uint8), _p(rf, C.c_double),
+                             _p(rewards, C.c_float) if want_rewards else None, _p(done, C.c_uint8), _p(obs, C.c_uint8))
             return
         # per-slice contiguous views: actions/rewards/done are [T,B,...] so slice-copy them
         act = np.ascontiguousarray(actions[:, lo:hi])
@@ -209,6 +236,18 @@ def actor_td(rew_fp16: np.ndarray, q: np.ndarray, act: np.ndarray, capacity: int
     a = np.ascontiguousarray(act, dtype=np.uint8)
     td = np.empty(capacity, dtype=np.float64)
     lib().mo_actor_td(size, capacity, _p(r, C.c_double), _p(qq, C.c_float), _p(a, C.c_uint8), _p(td, C.c_double))
+    return td
+
+
+def actor_td_n(rew_fp16: np.ndarray, q: np.ndarray, act: np.ndarray, capacity: int, forward_steps: int, gamma: float) -> np.ndarray:
+    """buffer.py:170-177 for config.forward_steps = n and discount gamma (the reference: n = 2, 0.99)."""
+    size = int(len(rew_fp16))
+    r = np.ascontiguousarray(rew_fp16, dtype=np.float64)
+    qq = np.ascontiguousarray(q, dtype=np.float32)
+    a = np.ascontiguousarray(act, dtype=np.uint8)
+    td = np.empty(capacity, dtype=np.float64)
+    lib().mo_actor_td_n(size, capacity, int(forward_steps), float(gamma), _p(r, C.c_double), _p(qq, C.c_float), _p(a, C.c_uint8),
+                        _p(td, C.c_double))
     return td
 
 

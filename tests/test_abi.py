@@ -24,7 +24,7 @@ def test_header_symbols_exported_and_bound():
         assert hasattr(lib, n), f"{n} declared in include/mapf_b200.h but not exported"
         assert n in _native.SIGNATURES, f"{n} has no ctypes signature in _native.SIGNATURES"
     assert set(_native.SIGNATURES) == set(names)
-    assert lib.mapf_abi_version() == 1
+    assert lib.mapf_abi_version() == _native.ABI_VERSION == 2
 
 
 def test_library_is_sm100a_only():
