@@ -52,3 +52,33 @@ def sum_over_ranks(value: float, device=None) -> float:
     t = torch.tensor([value], dtype=torch.float64, device=device if device is not None else "cpu")
     dist.all_reduce(t, op=dist.ReduceOp.SUM)
     return float(t.item())
+
+
+def gather_floats(value: float, device=None):
+    """One float per rank -> list over ranks (bench.py reports the per-rank spread of the timed region)."""
+    import torch
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return [float(value)]
+    t = torch.tensor([value], dtype=torch.float64, device=device if device is not None else "cpu")
+    out = [torch.zeros_like(t) for _ in range(dist.get_world_size())]
+    dist.all_gather(out, t)
+    return [float(x.item()) for x in out]
+
+
+def pin_to_cores(local_rank: int, local_world: int) -> list:
+    """Give every rank of one box its own contiguous slice of the host cores this process may run on (the host side of the
+    host-buffer step -- launch, flag poll -- otherwise migrates between cores that other ranks are spinning on).  Returns
+    the cores chosen ([] when the platform has no affinity call or there are fewer cores than ranks)."""
+    if local_world <= 1 or not hasattr(os, "sched_getaffinity"):
+        return []
+    try:
+        cores = sorted(os.sched_getaffinity(0))
+        per = len(cores) // local_world
+        if per < 1:
+            return []
+        mine = cores[local_rank * per:(local_rank + 1) * per]
+        os.sched_setaffinity(0, mine)
+        return mine
+    except OSError:
+        return []

@@ -205,6 +205,7 @@ def _rollout_vs_twin(env, twin, acts, T, A, R, S, want_codes=False, oracle_envs=
     done = torch.zeros((S, B), dtype=torch.uint8, device="cuda")
     steps = torch.zeros((S, B), dtype=torch.int32, device="cuda")
     maps, pos0, goals = env.map.cpu().numpy(), env.agents_pos.cpu().numpy(), env.goals_pos.cpu().numpy()
+    steps0 = env.steps.clone()
     env.rollout(acts, num_steps=T, out_obs=obs, out_rewards=rew, out_done=done, out_steps=steps, out_codes=codes)
     ora = []
     for k in sorted(set(min(k, B - 1) for k in oracle_envs) | {B - 1}):
@@ -229,7 +230,7 @@ def _rollout_vs_twin(env, twin, acts, T, A, R, S, want_codes=False, oracle_envs=
         if want_codes:
             assert int(codes[s].max()) <= 4 and torch.equal(table[codes[s].long()], exp_rew[s]), s
         last_t = max(t for t in range(T) if t % S == s)
-        assert torch.equal(steps[s], torch.full((B,), last_t + 1, dtype=torch.int32, device="cuda"))
+        assert torch.equal(steps[s], steps0 + (last_t + 1))
     assert torch.equal(env.agents_pos, twin.agents_pos) and torch.equal(env.steps, twin.steps)
 
 
