@@ -394,12 +394,13 @@ def run_ours(args):
     if cfg["actions"] == "greedy":
         pass                   # (the script was recorded from the state the env has been restored to; resets keep it "greedy-ish")
     sampler.start()
+    ep0 = int(env.episode_counts().sum()) if cap > 0 else 0
     ms_local = timed_rollout(K)
     env.check()
     ms_all = sharding.gather_floats(ms_local, dev)
     ms = max(ms_all)
     value = world * B * N * K / (ms * 1e-3)
-    resets_in_region = int((steps_ring[(K - 1) % out_ring] < torch.minimum(stagger + K, torch.full_like(stagger, 1 << 30))).sum()) if cap > 0 else 0
+    resets_in_region = int(sharding.sum_over_ranks((int(env.episode_counts().sum()) - ep0) if cap > 0 else 0, dev))
 
     # ---- the same K steps without episode handling (what round 1 timed) --------------------------------------------------
     arm(False)

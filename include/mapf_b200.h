@@ -180,6 +180,9 @@ int mapf_env_rollout_ex(mapf_env *env, const mapf_rollout_io *io, void *stream);
 int mapf_env_set_autoreset(mapf_env *env, int32_t max_steps, uint64_t seed, uint64_t env_offset, uint64_t stride,
                            float density, void *stream);
 
+/* d_counts_out u32[B]: instances generated for each slot by the episode handling since mapf_env_set_autoreset. */
+int mapf_env_episode_counts(mapf_env *env, uint32_t *d_counts_out, void *stream);
+
 /* check_unique != 0: every step verifies that no two agents share a cell afterwards (environment.py:424-428) and latches
  * MAPF_EUNIQUE otherwise (read by mapf_env_status).  Off by default: a correct step from a valid state cannot violate it,
  * and load / set_state validate what they are given. */

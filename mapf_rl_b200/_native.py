@@ -68,6 +68,7 @@ SIGNATURES = {
     "mapf_env_rollout_ex": (C.c_int, [_vp, C.POINTER(RolloutIO), _vp]),
     "mapf_env_set_autoreset": (C.c_int, [_vp, _i32, _u64, _u64, _u64, _f32, _vp]),
     "mapf_env_set_checks": (C.c_int, [_vp, _i32]),
+    "mapf_env_episode_counts": (C.c_int, [_vp, _vp, _vp]),
     "mapf_env_rollout_plan": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp]),
     "mapf_env_step_host": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "mapf_env_step_host_codes": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp]),

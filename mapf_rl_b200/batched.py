@@ -212,6 +212,13 @@ class BatchedEnvironment:
                                                       C.c_uint64(stride if stride is not None else self.num_envs),
                                                       C.c_float(dens), self._stream()))
 
+    def episode_counts(self):
+        """int32[B] CUDA tensor: instances generated for each slot by the episode handling since set_autoreset."""
+        torch = _torch()
+        out = torch.empty((self.num_envs,), dtype=torch.int32, device=self.device)
+        _native.check(self._lib.mapf_env_episode_counts(self._h, C.c_void_p(out.data_ptr()), self._stream()))
+        return out
+
     def set_checks(self, check_unique: bool = True):
         """Post-step uniqueness check of the agents' cells (environment.py:424-428) in every step; a violation raises
         RuntimeError('unique') from check()."""
@@ -255,14 +262,22 @@ class BatchedEnvironment:
         B, N = self.num_envs, self.num_agents
         hb = getattr(self, "_hb", None)
         if hb is None:
+            # codes | steps | done of step_host_codes in ONE page-locked block, laid out like the library's device staging
+            # (codes u8[B*N], pad to 16, steps i32[B], done u8[B]): the DMA form copies it back in one piece
+            off_steps = (B * N + 15) & ~15
+            off_done = off_steps + 4 * B
+            block = torch.empty((off_done + B,), dtype=torch.uint8, pin_memory=True)
             hb = dict(actions=torch.empty((B, N), dtype=torch.uint8, pin_memory=True),
                       rewards=torch.empty((B, N), dtype=torch.float32, pin_memory=True),
-                      codes=torch.empty((B, N), dtype=torch.uint8, pin_memory=True),
+                      codes=block[:B * N].view(B, N),
+                      cdone=block[off_done:off_done + B],
+                      csteps=block[off_steps:off_done].view(torch.int32),
                       done=torch.empty((B,), dtype=torch.uint8, pin_memory=True),
                       steps=torch.empty((B,), dtype=torch.int32, pin_memory=True))
-            hb.update({k + "_np": v.numpy() for k, v in list(hb.items())})
+            hb["_block"] = block
+            hb.update({k + "_np": v.numpy() for k, v in list(hb.items()) if not k.startswith("_")})
             hb["ptrs"] = tuple(C.c_void_p(hb[k].data_ptr()) for k in ("actions", "rewards", "done", "steps"))
-            hb["codes_ptr"] = C.c_void_p(hb["codes"].data_ptr())
+            hb["codes_ptrs"] = tuple(C.c_void_p(hb[k].data_ptr()) for k in ("codes", "cdone", "csteps"))
             self._hb = hb
         if want_obs and "obs" not in hb:
             hb["obs"] = torch.empty((B, N, *self.OBS_SHAPE), dtype=torch.uint8, pin_memory=True)
@@ -313,11 +328,11 @@ class BatchedEnvironment:
         stream.  Returns (codes uint8[B,N], done uint8[B], steps int32[B]) numpy VIEWS of page-locked buffers owned by this
         object (overwritten by the next call); rewards = reward_table[codes], see `reward_table`."""
         hb = self._host_buffers(False)
-        pa, _, pd, ps = hb["ptrs"]
-        pa = self._host_actions_ptr(actions, hb, pa)
-        _native.check(self._lib.mapf_env_step_host_codes(self._h, pa, hb["codes_ptr"], pd, ps, C.c_void_p(device_obs.data_ptr()),
+        pc, pd, ps = hb["codes_ptrs"]
+        pa = self._host_actions_ptr(actions, hb, hb["ptrs"][0])
+        _native.check(self._lib.mapf_env_step_host_codes(self._h, pa, pc, pd, ps, C.c_void_p(device_obs.data_ptr()),
                                                         self._stream()))
-        return hb["codes_np"], hb["done_np"], hb["steps_np"]
+        return hb["codes_np"], hb["cdone_np"], hb["csteps_np"]
 
     @property
     def reward_table(self) -> np.ndarray:

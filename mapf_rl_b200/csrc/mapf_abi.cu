@@ -13,8 +13,8 @@ int mapf_launch_pack_load(mapf_env *, const int32_t *, int, const uint8_t *, con
 int mapf_launch_validate_state(mapf_env *, const int32_t *, int, cudaStream_t);
 int mapf_launch_bfs(mapf_env *, const int32_t *, int, int32_t *, cudaStream_t);
 int mapf_launch_step(mapf_env *, const uint8_t *, uint8_t *, const int64_t *, const StepOut &, cudaStream_t);
-int mapf_launch_observe(mapf_env *, uint8_t *, const int64_t *, uint8_t *, cudaStream_t);
-int mapf_launch_step_only(mapf_env *, const uint8_t *, const StepOut &, cudaStream_t);
+int mapf_launch_observe(mapf_env *, uint8_t *, const int64_t *, uint8_t *, const uint8_t *, cudaStream_t);
+int mapf_launch_step_only(mapf_env *, const uint8_t *, const StepOut &, uint8_t *, cudaStream_t);
 int mapf_launch_step_range(mapf_env *, int, int, const uint8_t *, uint8_t *, const StepOut &, cudaStream_t);
 int mapf_launch_rollout(mapf_env *, int, int, int, const uint8_t *, int, uint8_t *, int, const StepOut &, int, cudaStream_t);
 bool mapf_rollout_supported(const mapf_env *);
@@ -192,13 +192,13 @@ int mapf_env_create(const mapf_env_config *cfg, mapf_env **out)
     if (rc == MAPF_OK) rc = dev_alloc(&env->ro_work, 2, &total);
     if (rc == MAPF_OK) rc = dev_alloc(&env->ro_progress, (size_t)d.B, &total);
     if (rc == MAPF_OK) rc = dev_alloc(&env->ro_episode, (size_t)d.B, &total);
-    if (rc == MAPF_OK) rc = dev_alloc(&env->pub_counter, 1, &total);
+    if (rc == MAPF_OK) rc = dev_alloc(&env->ro_prio, (size_t)d.B + 1, &total);
+    if (rc == MAPF_OK) rc = dev_alloc(&env->ro_prio_flag, (size_t)d.B, &total);
     if (rc == MAPF_OK) {
         cudaError_t e2 = cudaMemset(env->obst, 0, (size_t)d.B * d.obst_stride * 4);
         if (e2 == cudaSuccess) e2 = cudaMemset(env->ro_work, 0, 16);
         if (e2 == cudaSuccess) e2 = cudaMemset(env->ro_progress, 0, (size_t)d.B * 4);
         if (e2 == cudaSuccess) e2 = cudaMemset(env->ro_episode, 0, (size_t)d.B * 4);
-        if (e2 == cudaSuccess) e2 = cudaMemset(env->pub_counter, 0, 4);
         if (e2 == cudaSuccess) e2 = cudaMemset(env->pos, 0, BN * 2);
         if (e2 == cudaSuccess) e2 = cudaMemset(env->goal, 0, BN * 2);
         if (e2 == cudaSuccess) e2 = cudaMemset(env->navi, 0, BN * d.navi_agent_stride * 4);
@@ -229,14 +229,24 @@ int mapf_env_destroy(mapf_env *env)
     cudaFree(env->ro_work);
     cudaFree(env->ro_progress);
     cudaFree(env->ro_episode);
-    cudaFree(env->pub_counter);
+    cudaFree(env->hp_pos[0]);
+    cudaFree(env->hp_pos[1]);
+    cudaFree(env->hp_results);
+    if (env->hp_stream) cudaStreamDestroy(env->hp_stream);
+    for (int i = 0; i < 2; ++i) {
+        if (env->hp_step[i]) cudaEventDestroy(env->hp_step[i]);
+        if (env->hp_obs[i]) cudaEventDestroy(env->hp_obs[i]);
+    }
+    if (env->hp_in) cudaEventDestroy(env->hp_in);
+    if (env->hp_stepped) cudaEventDestroy(env->hp_stepped);
+    cudaFree(env->ro_prio);
+    cudaFree(env->ro_prio_flag);
     cudaFree(env->d_actions);
     cudaFree(env->d_obs);
     cudaFree(env->d_rewards);
     cudaFree(env->d_done);
     cudaFree(env->d_steps_out);
     if (env->h_pinned) cudaFreeHost(env->h_pinned);
-    if (env->h_flag) cudaFreeHost(const_cast<uint32_t *>(env->h_flag));
     for (auto &c : env->hg)
         if (c.exec) cudaGraphExecDestroy(c.exec);
     if (env->cap_stream) cudaStreamDestroy(env->cap_stream);
@@ -268,10 +278,29 @@ int64_t mapf_env_arena_bytes(const mapf_env *env) { return env ? env->arena_byte
         return MAPF_ECUDA;                        \
     }
 
+// Other entry points call this first: what the host-step pipeline still has in flight (step kernel on its internal stream,
+// observe kernel on the stream of the last call) is ordered before whatever they queue on `st`.
+static int hp_drain(mapf_env *env, cudaStream_t st)
+{
+    if (!env->hp_active) return MAPF_OK;
+    for (int i = 0; i < 2; ++i) {
+        MAPF_CUDA(cudaStreamWaitEvent(st, env->hp_step[i], 0));
+        MAPF_CUDA(cudaStreamWaitEvent(st, env->hp_obs[i], 0));
+    }
+    env->hp_active = 0;
+    return MAPF_OK;
+}
+#define MAPF_DRAIN(env, st)                         \
+    do {                                            \
+        const int _rc = hp_drain((env), (st));      \
+        if (_rc != MAPF_OK) return _rc;             \
+    } while (0)
+
 int mapf_env_load(mapf_env *env, const int32_t *d_env_ids, int32_t n, const uint8_t *d_maps, const uint8_t *d_agents,
                   const uint8_t *d_goals, void *stream)
 {
     REQUIRE_ENV(env);
+    MAPF_DRAIN(env, static_cast<cudaStream_t>(stream));
     if (n < 0 || n > env->d.B || !d_maps || !d_agents || !d_goals) {
         mapf_set_error("mapf_env_load: bad arguments");
         return MAPF_EINVAL;
@@ -288,6 +317,7 @@ int mapf_env_load(mapf_env *env, const int32_t *d_env_ids, int32_t n, const uint
 int mapf_env_bfs_navi(mapf_env *env, const int32_t *d_env_ids, int32_t n, int32_t *d_dist_out, void *stream)
 {
     REQUIRE_ENV(env);
+    MAPF_DRAIN(env, static_cast<cudaStream_t>(stream));
     if (!d_env_ids) n = env->d.B;
     if (n < 0 || n > env->d.B) {
         mapf_set_error("mapf_env_bfs_navi: bad n");
@@ -301,6 +331,7 @@ int mapf_env_step_observe_ex(mapf_env *env, const uint8_t *d_actions, uint8_t *d
                              uint8_t *d_codes, uint8_t *d_done, int32_t *d_steps, void *stream)
 {
     REQUIRE_ENV(env);
+    MAPF_DRAIN(env, static_cast<cudaStream_t>(stream));
     if (!d_actions || !d_obs || !d_done) {
         mapf_set_error("mapf_env_step_observe: NULL buffer");
         return MAPF_EINVAL;
@@ -333,21 +364,23 @@ int mapf_env_step_observe_rows(mapf_env *env, const uint8_t *d_actions, uint8_t 
 int mapf_env_observe_rows(mapf_env *env, uint8_t *d_obs_base, const int64_t *d_obs_rows, uint8_t *d_pos, void *stream)
 {
     REQUIRE_ENV(env);
+    MAPF_DRAIN(env, static_cast<cudaStream_t>(stream));
     if (!d_obs_base || !d_obs_rows) {
         mapf_set_error("mapf_env_observe_rows: NULL buffer");
         return MAPF_EINVAL;
     }
-    return mapf_launch_observe(env, d_obs_base, d_obs_rows, d_pos, static_cast<cudaStream_t>(stream));
+    return mapf_launch_observe(env, d_obs_base, d_obs_rows, d_pos, nullptr, static_cast<cudaStream_t>(stream));
 }
 
 int mapf_env_observe(mapf_env *env, uint8_t *d_obs, uint8_t *d_pos, void *stream)
 {
     REQUIRE_ENV(env);
+    MAPF_DRAIN(env, static_cast<cudaStream_t>(stream));
     if (!d_obs) {
         mapf_set_error("mapf_env_observe: NULL buffer");
         return MAPF_EINVAL;
     }
-    return mapf_launch_observe(env, d_obs, nullptr, d_pos, static_cast<cudaStream_t>(stream));
+    return mapf_launch_observe(env, d_obs, nullptr, d_pos, nullptr, static_cast<cudaStream_t>(stream));
 }
 
 namespace {
@@ -415,6 +448,7 @@ int mapf_env_rollout_plan(mapf_env *env, int32_t T, int32_t action_slots, int32_
 int mapf_env_rollout_ex(mapf_env *env, const mapf_rollout_io *io, void *stream)
 {
     REQUIRE_ENV(env);
+    MAPF_DRAIN(env, static_cast<cudaStream_t>(stream));
     if (!io || !io->d_actions || !io->d_obs || !io->d_done) {
         mapf_set_error("mapf_env_rollout: NULL buffer");
         return MAPF_EINVAL;
@@ -558,6 +592,7 @@ int mapf_env_set_autoreset(mapf_env *env, int32_t max_steps, uint64_t seed, uint
                            void *stream)
 {
     REQUIRE_ENV(env);
+    MAPF_DRAIN(env, static_cast<cudaStream_t>(stream));
     if (max_steps < 0 || density >= 1.0f) {
         mapf_set_error("mapf_env_set_autoreset: max_steps >= 0 and density < 1 required");
         return MAPF_EINVAL;
@@ -573,6 +608,18 @@ int mapf_env_set_autoreset(mapf_env *env, int32_t max_steps, uint64_t seed, uint
     return MAPF_OK;
 }
 
+int mapf_env_episode_counts(mapf_env *env, uint32_t *d_counts_out, void *stream)
+{
+    REQUIRE_ENV(env);
+    MAPF_DRAIN(env, static_cast<cudaStream_t>(stream));
+    if (!d_counts_out) {
+        mapf_set_error("mapf_env_episode_counts: NULL buffer");
+        return MAPF_EINVAL;
+    }
+    MAPF_CUDA(cudaMemcpyAsync(d_counts_out, env->ro_episode, (size_t)env->d.B * 4, cudaMemcpyDeviceToDevice, static_cast<cudaStream_t>(stream)));
+    return MAPF_OK;
+}
+
 int mapf_env_set_checks(mapf_env *env, int32_t check_unique)
 {
     REQUIRE_ENV(env);
@@ -585,6 +632,7 @@ int mapf_env_step_host(mapf_env *env, const uint8_t *h_actions, uint8_t *h_obs, 
                        int32_t *h_steps, uint8_t *d_obs_opt, void *stream)
 {
     REQUIRE_ENV(env);
+    MAPF_DRAIN(env, static_cast<cudaStream_t>(stream));
     if (!h_actions || !h_rewards || !h_done) {
         mapf_set_error("mapf_env_step_host: NULL buffer");
         return MAPF_EINVAL;
@@ -642,7 +690,7 @@ int mapf_env_step_host(mapf_env *env, const uint8_t *h_actions, uint8_t *h_obs, 
         }
         StepOut o;
         o.rewards = env->d_rewards, o.done = env->d_done, o.steps = env->d_steps_out;
-        int r = mapf_launch_step_only(env, a, o, q);
+        int r = mapf_launch_step_only(env, a, o, nullptr, q);
         if (r != MAPF_OK) return r;
         MAPF_CUDA(cudaEventRecord(env->ev_stepped, q));
         MAPF_CUDA(cudaStreamWaitEvent(env->side_stream, env->ev_stepped, 0));
@@ -651,7 +699,7 @@ int mapf_env_step_host(mapf_env *env, const uint8_t *h_actions, uint8_t *h_obs, 
             MAPF_CUDA(cudaMemcpyAsync(dst_steps, env->d_steps_out, (size_t)d.B * 4, cudaMemcpyDeviceToHost, env->side_stream));
         MAPF_CUDA(cudaMemcpyAsync(dst_done, env->d_done, (size_t)d.B, cudaMemcpyDeviceToHost, env->side_stream));
         MAPF_CUDA(cudaEventRecord(env->ev_copied, env->side_stream));
-        r = mapf_launch_observe(env, obs_dev, nullptr, nullptr, q);
+        r = mapf_launch_observe(env, obs_dev, nullptr, nullptr, nullptr, q);
         if (r != MAPF_OK) return r;
         if (h_obs) MAPF_CUDA(cudaMemcpyAsync(h_obs, obs_dev, BN * MAPF_OBS_BYTES_PER_AGENT, cudaMemcpyDeviceToHost, q));
         MAPF_CUDA(cudaStreamWaitEvent(q, env->ev_copied, 0));
@@ -711,68 +759,118 @@ int mapf_env_step_host_codes(mapf_env *env, const uint8_t *h_actions, uint8_t *h
     }
     const EnvDims &d = env->d;
     const size_t BN = (size_t)d.B * d.N;
+    const size_t off_steps = (BN + 15) & ~(size_t)15, off_done = off_steps + (size_t)d.B * 4;
+    const size_t res_bytes = off_done + d.B;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (!env->hp_stream) {
+        int64_t total = env->arena_bytes;
+        int rc = dev_alloc(&env->hp_pos[0], BN * 2, &total);
+        if (rc == MAPF_OK) rc = dev_alloc(&env->hp_pos[1], BN * 2, &total);
+        if (rc == MAPF_OK) rc = dev_alloc(&env->hp_results, res_bytes + 16, &total);
+        env->arena_bytes = total;
+        if (rc != MAPF_OK) return rc;
+        MAPF_CUDA(cudaStreamCreateWithFlags(&env->hp_stream, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; ++i) {
+            MAPF_CUDA(cudaEventCreateWithFlags(&env->hp_step[i], cudaEventDisableTiming));
+            MAPF_CUDA(cudaEventCreateWithFlags(&env->hp_obs[i], cudaEventDisableTiming));
+        }
+        MAPF_CUDA(cudaEventCreateWithFlags(&env->hp_in, cudaEventDisableTiming));
+        MAPF_CUDA(cudaEventCreateWithFlags(&env->hp_stepped, cudaEventDisableTiming));
+    }
     if (!env->h_pinned) {
         cudaError_t e = cudaMallocHost(reinterpret_cast<void **>(&env->h_pinned), BN + BN * 4 + (size_t)d.B * 5 + 128);
         if (e != cudaSuccess) return mapf_cuda_fail(e, "cudaMallocHost");
     }
-    if (!env->h_flag) {
-        void *flag = nullptr;
-        cudaError_t e = cudaMallocHost(&flag, 64);
-        if (e != cudaSuccess) return mapf_cuda_fail(e, "cudaMallocHost");
-        env->h_flag = static_cast<volatile uint32_t *>(flag);
-        *env->h_flag = 0;
-        env->d_flag = host_device_alias(const_cast<uint32_t *>(env->h_flag));
-        if (!env->d_flag) {
-            mapf_set_error("mapf_env_step_host_codes: page-locked host memory is not mapped into the device address space");
-            return MAPF_ECUDA;
-        }
-    }
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
-    // staging layout for pageable caller buffers: actions u8[BN] | pad | codes u8[BN] | pad | steps i32[B] | done u8[B]
+    // pinned staging for pageable caller buffers: actions u8[BN] | pad | results (codes | steps | done, as on the device)
     uint8_t *pin_act = env->h_pinned;
-    uint8_t *pin_codes = env->h_pinned + ((BN + 15) & ~(size_t)15);
-    int32_t *pin_steps = reinterpret_cast<int32_t *>(pin_codes + ((BN + 15) & ~(size_t)15));
-    uint8_t *pin_done = reinterpret_cast<uint8_t *>(pin_steps + d.B);
-    const uint8_t *act_alias = pinned_alias(h_actions);
-    if (!act_alias) {
+    uint8_t *pin_res = env->h_pinned + ((BN + 15) & ~(size_t)15);
+    // MAPF_HOSTCODES_MODE: 1 (default) = device staging + DMA copies (ONE contiguous copy when the caller's three buffers are
+    // laid out like the staging: codes | pad to 16 | steps | done), 0 = the step kernel stores its results straight into
+    // page-locked host memory (measured: 56 us against 42 us latency per call, the scattered 32-byte PCIe writes cost more
+    // than the one DMA; profiles/r2_e2e_probe.jsonl)
+    static const int copy_mode = [] { const char *v = std::getenv("MAPF_HOSTCODES_MODE"); return v ? std::atoi(v) : 1; }();
+    const uint8_t *act_alias = pinned_alias(h_actions);   // the only query on the critical path: the kernel launch follows
+    const bool act_direct = act_alias != nullptr;
+    if (!act_direct) {
         std::memcpy(pin_act, h_actions, BN);
         act_alias = host_device_alias(pin_act);
     }
-    uint8_t *codes_alias = pinned_alias(h_codes), *done_alias = pinned_alias(h_done);
-    int32_t *steps_alias = h_steps ? pinned_alias(h_steps) : nullptr;
-    const bool out_direct = codes_alias && done_alias && (!h_steps || steps_alias);
-    if (!out_direct) {
-        codes_alias = host_device_alias(pin_codes), done_alias = host_device_alias(pin_done);
-        steps_alias = h_steps ? host_device_alias(pin_steps) : nullptr;
+    // a new run of the pipeline: the step stream starts after what the caller has queued on `st` (a reset, a load, ...)
+    if (!env->hp_active) {
+        MAPF_CUDA(cudaEventRecord(env->hp_in, st));
+        MAPF_CUDA(cudaStreamWaitEvent(env->hp_stream, env->hp_in, 0));
+        env->hp_t = 0;
+        env->hp_active = 1;
     }
-    if (!act_alias || !codes_alias || !done_alias) {
-        mapf_set_error("mapf_env_step_host_codes: page-locked host memory is not mapped into the device address space");
-        return MAPF_ECUDA;
+    const int slot = (int)(env->hp_t & 1);
+    // the observe kernel of two calls ago has read the snapshot this step overwrites
+    if (env->hp_t >= 2) MAPF_CUDA(cudaStreamWaitEvent(env->hp_stream, env->hp_obs[slot], 0));
+    // where the kernel writes its results: the caller's page-locked buffers (or the pinned staging area) in place, or the
+    // device staging block
+    uint8_t *codes_alias = nullptr, *done_alias = nullptr;
+    int32_t *steps_alias = nullptr;
+    bool out_direct = false;
+    if (copy_mode == 0) {
+        codes_alias = pinned_alias(h_codes), done_alias = pinned_alias(h_done);
+        steps_alias = h_steps ? pinned_alias(h_steps) : nullptr;
+        out_direct = codes_alias && done_alias && (!h_steps || steps_alias);
+        if (!out_direct) {
+            codes_alias = host_device_alias(pin_res), done_alias = host_device_alias(pin_res + off_done);
+            steps_alias = reinterpret_cast<int32_t *>(host_device_alias(pin_res + off_steps));
+        }
+    } else {
+        out_direct = host_is_pinned(h_codes) && host_is_pinned(h_done) && (!h_steps || host_is_pinned(h_steps));
     }
+    const bool zero_copy = copy_mode == 0 && codes_alias && done_alias && (steps_alias || (out_direct && !h_steps));
     StepOut o;
-    o.codes = codes_alias, o.done = done_alias, o.steps = steps_alias;
-    o.pub.counter = env->pub_counter;
-    o.pub.flag = env->d_flag;
-    o.pub.seq = ++env->pub_seq ? env->pub_seq : ++env->pub_seq;  // never 0
-    const int rc = mapf_launch_step(env, act_alias, d_obs, nullptr, o, st);
+    if (zero_copy) {
+        o.codes = codes_alias, o.done = done_alias, o.steps = h_steps || !out_direct ? steps_alias : nullptr;
+    } else {
+        o.codes = env->hp_results;
+        o.steps = reinterpret_cast<int32_t *>(env->hp_results + off_steps);
+        o.done = env->hp_results + off_done;
+    }
+    int rc;
+    if (act_alias) {
+        rc = mapf_launch_step_only(env, act_alias, o, env->hp_pos[slot], env->hp_stream);  // reads the actions in place over PCIe
+    } else {
+        if (!env->d_actions) {
+            int64_t total = env->arena_bytes;
+            rc = dev_alloc(&env->d_actions, BN, &total);
+            env->arena_bytes = total;
+            if (rc != MAPF_OK) return rc;
+        }
+        MAPF_CUDA(cudaMemcpyAsync(env->d_actions, act_direct ? h_actions : pin_act, BN, cudaMemcpyHostToDevice, env->hp_stream));
+        rc = mapf_launch_step_only(env, env->d_actions, o, env->hp_pos[slot], env->hp_stream);
+    }
     if (rc != MAPF_OK) return rc;
-    // wait for the flag, not for the kernel: the observation stores keep draining on `st`
-    const uint32_t want = o.pub.seq;
-    unsigned spins = 0;
-    while (*env->h_flag != want) {
-        if ((++spins & 0x3fff) == 0) {  // every ~16k polls: has the stream died (launch failure, sticky error)?
-            const cudaError_t q = cudaStreamQuery(st);
-            if (q != cudaErrorNotReady && q != cudaSuccess) return mapf_cuda_fail(q, "mapf_env_step_host_codes (kernel)");
-            if (q == cudaSuccess && *env->h_flag != want) {
-                mapf_set_error("mapf_env_step_host_codes: the kernel finished without raising the host flag");
-                return MAPF_ECUDA;
-            }
+    // stage 2 on the caller's stream starts as soon as the step kernel is done (the result copies run next to it): the
+    // observation of the snapshot, ordered before anything queued on `st` afterwards
+    MAPF_CUDA(cudaEventRecord(env->hp_stepped, env->hp_stream));
+    MAPF_CUDA(cudaStreamWaitEvent(st, env->hp_stepped, 0));
+    rc = mapf_launch_observe(env, d_obs, nullptr, nullptr, env->hp_pos[slot], st);
+    if (rc != MAPF_OK) return rc;
+    MAPF_CUDA(cudaEventRecord(env->hp_obs[slot], st));
+    if (!zero_copy) {
+        const bool contiguous = out_direct && h_steps && reinterpret_cast<uint8_t *>(h_steps) == h_codes + off_steps && h_done == h_codes + off_done;
+        if (contiguous) {
+            MAPF_CUDA(cudaMemcpyAsync(h_codes, env->hp_results, res_bytes, cudaMemcpyDeviceToHost, env->hp_stream));
+        } else if (out_direct) {
+            MAPF_CUDA(cudaMemcpyAsync(h_codes, env->hp_results, BN, cudaMemcpyDeviceToHost, env->hp_stream));
+            if (h_steps) MAPF_CUDA(cudaMemcpyAsync(h_steps, env->hp_results + off_steps, (size_t)d.B * 4, cudaMemcpyDeviceToHost, env->hp_stream));
+            MAPF_CUDA(cudaMemcpyAsync(h_done, env->hp_results + off_done, (size_t)d.B, cudaMemcpyDeviceToHost, env->hp_stream));
+        } else {
+            MAPF_CUDA(cudaMemcpyAsync(pin_res, env->hp_results, res_bytes, cudaMemcpyDeviceToHost, env->hp_stream));
         }
     }
+    MAPF_CUDA(cudaEventRecord(env->hp_step[slot], env->hp_stream));
+    env->hp_t++;
+    // the results are on the host when stage 1 is done; the observe kernel keeps running
+    MAPF_CUDA(cudaEventSynchronize(env->hp_step[slot]));
     if (!out_direct) {
-        std::memcpy(h_codes, pin_codes, BN);
-        std::memcpy(h_done, pin_done, (size_t)d.B);
-        if (h_steps) std::memcpy(h_steps, pin_steps, (size_t)d.B * 4);
+        std::memcpy(h_codes, pin_res, BN);
+        std::memcpy(h_done, pin_res + off_done, (size_t)d.B);
+        if (h_steps) std::memcpy(h_steps, pin_res + off_steps, (size_t)d.B * 4);
     }
     return MAPF_OK;
 }
@@ -799,6 +897,7 @@ int mapf_debug_step_host_mode(int32_t mode)
 int mapf_env_comm_mask(mapf_env *env, int32_t max_comm_agents, uint8_t *d_mask_out, void *stream)
 {
     REQUIRE_ENV(env);
+    MAPF_DRAIN(env, static_cast<cudaStream_t>(stream));
     if (!d_mask_out || max_comm_agents < 1 || max_comm_agents > 3) {
         mapf_set_error("mapf_env_comm_mask: NULL buffer or max_comm_agents outside 1..3 (config.py:58)");
         return MAPF_EINVAL;
@@ -810,6 +909,7 @@ int mapf_env_get_state(mapf_env *env, uint8_t *d_map, uint8_t *d_pos, uint8_t *d
                        void *stream)
 {
     REQUIRE_ENV(env);
+    MAPF_DRAIN(env, static_cast<cudaStream_t>(stream));
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const size_t BN2 = (size_t)env->d.B * env->d.N * 2;
     if (d_pos) MAPF_CUDA(cudaMemcpyAsync(d_pos, env->pos, BN2, cudaMemcpyDeviceToDevice, st));
@@ -821,6 +921,7 @@ int mapf_env_get_state(mapf_env *env, uint8_t *d_map, uint8_t *d_pos, uint8_t *d
 int mapf_env_set_state(mapf_env *env, const uint8_t *d_pos, const int32_t *d_steps, void *stream)
 {
     REQUIRE_ENV(env);
+    MAPF_DRAIN(env, static_cast<cudaStream_t>(stream));
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (d_pos) {
         MAPF_CUDA(cudaMemcpyAsync(env->pos, d_pos, (size_t)env->d.B * env->d.N * 2, cudaMemcpyDeviceToDevice, st));
@@ -834,6 +935,7 @@ int mapf_env_set_state(mapf_env *env, const uint8_t *d_pos, const int32_t *d_ste
 int mapf_env_status(mapf_env *env, void *stream)
 {
     REQUIRE_ENV(env);
+    MAPF_DRAIN(env, static_cast<cudaStream_t>(stream));
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     int32_t bits = 0;
     MAPF_CUDA(cudaMemcpyAsync(&bits, env->err, 4, cudaMemcpyDeviceToHost, st));
@@ -868,6 +970,7 @@ int mapf_env_status(mapf_env *env, void *stream)
 int mapf_env_reset(mapf_env *env, const uint8_t *d_mask, uint64_t seed, uint64_t env_offset, float density, void *stream)
 {
     REQUIRE_ENV(env);
+    MAPF_DRAIN(env, static_cast<cudaStream_t>(stream));
     if (density >= 1.0f) {
         mapf_set_error("mapf_env_reset: density must be < 1");
         return MAPF_EINVAL;

@@ -21,160 +21,137 @@
 
 namespace {
 
+// state of one agent's search in its lanes' registers
+template <int RW, int RPL>
+struct BfsState {
+    uint32_t unv[RPL][RW];  // free and not yet visited
+    uint32_t fro[RPL][RW];  // frontier of the previous wave
+    uint32_t m1[RPL][RW];   // cells whose wave number is 1 mod 3
+    uint32_t m2[RPL][RW];   // ... 2 mod 3 (reached cells in neither: 0 mod 3)
+};
+
+// in-map column mask of word w: padded bits [4, L + 4)
+__device__ __forceinline__ uint32_t bfs_column_mask(int L, int w)
+{
+    const int lo = max(4 - 32 * w, 0), hi = min(L + 4 - 32 * w, 32);
+    if (hi <= lo) return 0u;
+    return (hi - lo == 32) ? 0xffffffffu : (((1u << (hi - lo)) - 1u) << lo);
+}
+
 template <int RW, int RPL, int APW>
-__device__ __forceinline__ void bfs_navi_warp(const EnvDims &d, const int e, const int a, const int i, const bool alive,
-                                              const uint32_t *__restrict__ obst, const uint8_t *__restrict__ goal,
-                                              uint32_t *__restrict__ navi, int32_t *__restrict__ dist_out)
+__device__ __forceinline__ void bfs_init(const EnvDims &d, const uint32_t *ob, const int gx, const int gy, const bool alive,
+                                         BfsState<RW, RPL> &S)
 {
     constexpr int LW = 32 / APW;
     const int lane = (threadIdx.x & 31) % LW;    // lane within the agent's group
-    const uint32_t *ob = obst + (size_t)e * d.obst_stride;
-
-    // unv = free and not yet visited, fro = frontier of the previous wave, pl = the four heuristic planes
-    uint32_t unv[RPL][RW], fro[RPL][RW], pl[4][RPL][RW];
-    const uchar2 gg = __ldcg(reinterpret_cast<const uchar2 *>(goal) + (size_t)e * d.N + a);
-    const int gx = gg.x, gy = gg.y;
 #pragma unroll
     for (int q = 0; q < RPL; ++q) {
         const int row = alive ? lane * RPL + q : d.L;  // a group without an agent owns no rows
 #pragma unroll
         for (int w = 0; w < RW; ++w) {
-            // in-map column mask for this word: padded bits [4, L+4)
-            int lo = max(4 - 32 * w, 0), hi = min(d.L + 4 - 32 * w, 32);
-            uint32_t cm = 0;
-            if (hi > lo) cm = (hi - lo == 32) ? 0xffffffffu : (((1u << (hi - lo)) - 1u) << lo);
-            const uint32_t fre = (row < d.L) ? (~__ldcg(ob + (row + 4) * d.RWS + w) & cm) : 0u;
+            const uint32_t fre = (row < d.L) ? (~__ldcg(ob + (row + 4) * d.RWS + w) & bfs_column_mask(d.L, w)) : 0u;
             const int p = gy + 4;
-            fro[q][w] = (row == gx && (p >> 5) == w) ? ((1u << (p & 31)) & fre) : 0u;
-            unv[q][w] = fre & ~fro[q][w];
-#pragma unroll
-            for (int k = 0; k < 4; ++k) pl[k][q][w] = 0;
+            S.fro[q][w] = (row == gx && (p >> 5) == w) ? ((1u << (p & 31)) & fre) : 0u;
+            S.unv[q][w] = fre & ~S.fro[q][w];
+            S.m1[q][w] = S.m2[q][w] = 0;
         }
     }
+}
 
-    int32_t *dist = (dist_out && alive) ? dist_out + ((size_t)i * d.N + a) * d.L * d.L : nullptr;
-    if (dist_out) {
+// One wave: nw = (frontier shifted to the four neighbours) & free-and-unvisited; returns the OR of this lane's words.
+template <int RW, int RPL, int APW>
+__device__ __forceinline__ uint32_t bfs_wave(const BfsState<RW, RPL> &S, uint32_t (&nw)[RPL][RW])
+{
+    constexpr int LW = 32 / APW;
+    const int lane = (threadIdx.x & 31) % LW;
+    uint32_t any = 0;
+#pragma unroll
+    for (int w = 0; w < RW; ++w) {
+        // rows of the neighbouring lanes that touch this lane's block
+        uint32_t above = __shfl_up_sync(MAPF_FULL_MASK, S.fro[RPL - 1][w], 1, LW);
+        uint32_t below = __shfl_down_sync(MAPF_FULL_MASK, S.fro[0][w], 1, LW);
+        if (lane == 0) above = 0;
+        if (lane == LW - 1) below = 0;
+#pragma unroll
         for (int q = 0; q < RPL; ++q) {
-            const int row = lane * RPL + q;
-            if (dist && row < d.L)
-                for (int y = 0; y < d.L; ++y) dist[row * d.L + y] = MAPF_DIST_UNREACHABLE;
+            const uint32_t f = S.fro[q][w];
+            const uint32_t fl = w > 0 ? __funnelshift_l(S.fro[q][w > 0 ? w - 1 : 0], f, 1) : f << 1;
+            const uint32_t fr = w < RW - 1 ? __funnelshift_r(f, S.fro[q][w < RW - 1 ? w + 1 : w], 1) : f >> 1;
+            const uint32_t up = q > 0 ? S.fro[q > 0 ? q - 1 : 0][w] : above;
+            const uint32_t dn = q < RPL - 1 ? S.fro[q < RPL - 1 ? q + 1 : q][w] : below;
+            const uint32_t x = (fl | fr | up | dn) & S.unv[q][w];
+            nw[q][w] = x;
+            any |= x;
         }
-        __syncwarp();
-#pragma unroll
-        for (int q = 0; q < RPL; ++q)
-#pragma unroll
-            for (int w = 0; w < RW; ++w)
-                if (dist && fro[q][w]) dist[gx * d.L + gy] = 0;
     }
+    return any;
+}
 
-    // Wavefront loop.  Adjacent reachable cells of a 4-connected grid differ by exactly one in distance, so "the
-    // neighbour is strictly closer" (environment.py:260-274) is "its distance mod 3 is mine minus one": the loop only
-    // records WHICH residue a cell's wave had (m1 / m2; residue 0 = reached and in neither) -- one LOP per word and wave
-    // instead of four plane updates -- and the four planes are derived once at the end.
-    uint32_t m1[RPL][RW], m2[RPL][RW];
+template <int RW, int RPL, int SEL>
+__device__ __forceinline__ void bfs_apply(BfsState<RW, RPL> &S, const uint32_t (&nw)[RPL][RW])
+{
 #pragma unroll
     for (int q = 0; q < RPL; ++q)
 #pragma unroll
-        for (int w = 0; w < RW; ++w) m1[q][w] = m2[q][w] = 0;
-    auto wave = [&](auto selc, const int t) -> bool {
-        constexpr int sel = decltype(selc)::value;  // t mod 3
-        uint32_t nw[RPL][RW];
-        uint32_t any = 0;
+        for (int w = 0; w < RW; ++w) {
+            S.unv[q][w] &= ~nw[q][w];
+            S.fro[q][w] = nw[q][w];
+            if constexpr (SEL == 1) S.m1[q][w] |= nw[q][w];
+            if constexpr (SEL == 2) S.m2[q][w] |= nw[q][w];
+        }
+}
+
+// The four heuristic planes from the residues -- with z = reached cells of residue 0, "neighbour n is closer" holds at a
+// cell c iff (c in m1, n in z) or (c in m2, n in m1) or (c in z, n in m2) -- emitted as the overlapping 16x16 tiles
+// (mapf_common.cuh): a map row is padded row pr = row + 4, which is row pr & 7 of tile row-block pr >> 3 and row
+// (pr & 7) + 8 of the block above.
+template <int RW, int RPL, int APW>
+__device__ __forceinline__ void bfs_emit(const EnvDims &d, const uint32_t *ob, const int e, const int a, const bool alive,
+                                         const BfsState<RW, RPL> &S, uint32_t *__restrict__ navi)
+{
+    constexpr int LW = 32 / APW;
+    const int lane = (threadIdx.x & 31) % LW;
+    uint32_t pl[4][RPL][RW];
+    uint32_t z[RPL][RW];
+#pragma unroll
+    for (int q = 0; q < RPL; ++q) {
+        const int row = alive ? lane * RPL + q : d.L;
 #pragma unroll
         for (int w = 0; w < RW; ++w) {
-            // rows of the neighbouring lanes that touch this lane's block
-            uint32_t above = __shfl_up_sync(MAPF_FULL_MASK, fro[RPL - 1][w], 1, LW);
-            uint32_t below = __shfl_down_sync(MAPF_FULL_MASK, fro[0][w], 1, LW);
-            if (lane == 0) above = 0;
-            if (lane == LW - 1) below = 0;
-#pragma unroll
-            for (int q = 0; q < RPL; ++q) {
-                const uint32_t f = fro[q][w];
-                const uint32_t fl = w > 0 ? __funnelshift_l(fro[q][w > 0 ? w - 1 : 0], f, 1) : f << 1;
-                const uint32_t fr = w < RW - 1 ? __funnelshift_r(f, fro[q][w < RW - 1 ? w + 1 : w], 1) : f >> 1;
-                const uint32_t up = q > 0 ? fro[q > 0 ? q - 1 : 0][w] : above;
-                const uint32_t dn = q < RPL - 1 ? fro[q < RPL - 1 ? q + 1 : q][w] : below;
-                const uint32_t x = (fl | fr | up | dn) & unv[q][w];
-                nw[q][w] = x;
-                any |= x;
-            }
+            const uint32_t fre = (row < d.L) ? (~__ldcg(ob + (row + 4) * d.RWS + w) & bfs_column_mask(d.L, w)) : 0u;
+            z[q][w] = fre & ~S.unv[q][w] & ~S.m1[q][w] & ~S.m2[q][w];
         }
-        if (!__any_sync(MAPF_FULL_MASK, any != 0)) return false;
-#pragma unroll
-        for (int q = 0; q < RPL; ++q)
-#pragma unroll
-            for (int w = 0; w < RW; ++w) {
-                unv[q][w] &= ~nw[q][w];
-                fro[q][w] = nw[q][w];
-                if constexpr (sel == 1) m1[q][w] |= nw[q][w];
-                if constexpr (sel == 2) m2[q][w] |= nw[q][w];
-                if (dist_out) {  // a kernel argument: the loop is compiled twice, the common one without any of this
-                    uint32_t x = dist ? nw[q][w] : 0u;
-                    while (x) {
-                        int b = __ffs(x) - 1;
-                        x &= x - 1;
-                        dist[(lane * RPL + q) * d.L + (32 * w + b - 4)] = t;
-                    }
-                }
-            }
-        return true;
-    };
-    for (int t = 1;; t += 3) {
-        if (!wave(std::integral_constant<int, 1>{}, t)) break;
-        if (!wave(std::integral_constant<int, 2>{}, t + 1)) break;
-        if (!wave(std::integral_constant<int, 0>{}, t + 2)) break;
     }
-
-    // The four heuristic planes from the residues: with z = reached cells of residue 0, direction "neighbour n is
-    // closer" holds at a cell c iff (c in m1, n in z) or (c in m2, n in m1) or (c in z, n in m2).
-    {
-        uint32_t z[RPL][RW];
+    auto closer = [](uint32_t c1, uint32_t c2, uint32_t cz, uint32_t n1, uint32_t n2, uint32_t nz) -> uint32_t {
+        return (c1 & nz) | (c2 & n1) | (cz & n2);
+    };
+#pragma unroll
+    for (int w = 0; w < RW; ++w) {
+        // residue rows of the neighbouring lanes that touch this lane's block
+        uint32_t a1 = __shfl_up_sync(MAPF_FULL_MASK, S.m1[RPL - 1][w], 1, LW), b1 = __shfl_down_sync(MAPF_FULL_MASK, S.m1[0][w], 1, LW);
+        uint32_t a2 = __shfl_up_sync(MAPF_FULL_MASK, S.m2[RPL - 1][w], 1, LW), b2 = __shfl_down_sync(MAPF_FULL_MASK, S.m2[0][w], 1, LW);
+        uint32_t az = __shfl_up_sync(MAPF_FULL_MASK, z[RPL - 1][w], 1, LW), bz = __shfl_down_sync(MAPF_FULL_MASK, z[0][w], 1, LW);
+        if (lane == 0) a1 = a2 = az = 0;
+        if (lane == LW - 1) b1 = b2 = bz = 0;
 #pragma unroll
         for (int q = 0; q < RPL; ++q) {
-            const int row = alive ? lane * RPL + q : d.L;
-#pragma unroll
-            for (int w = 0; w < RW; ++w) {
-                int lo = max(4 - 32 * w, 0), hi = min(d.L + 4 - 32 * w, 32);
-                uint32_t cm = 0;
-                if (hi > lo) cm = (hi - lo == 32) ? 0xffffffffu : (((1u << (hi - lo)) - 1u) << lo);
-                const uint32_t fre = (row < d.L) ? (~__ldcg(ob + (row + 4) * d.RWS + w) & cm) : 0u;
-                z[q][w] = fre & ~unv[q][w] & ~m1[q][w] & ~m2[q][w];
-            }
-        }
-        auto closer = [](uint32_t c1, uint32_t c2, uint32_t cz, uint32_t n1, uint32_t n2, uint32_t nz) -> uint32_t {
-            return (c1 & nz) | (c2 & n1) | (cz & n2);
-        };
-#pragma unroll
-        for (int w = 0; w < RW; ++w) {
-            // residue rows of the neighbouring lanes that touch this lane's block
-            uint32_t a1 = __shfl_up_sync(MAPF_FULL_MASK, m1[RPL - 1][w], 1, LW), b1 = __shfl_down_sync(MAPF_FULL_MASK, m1[0][w], 1, LW);
-            uint32_t a2 = __shfl_up_sync(MAPF_FULL_MASK, m2[RPL - 1][w], 1, LW), b2 = __shfl_down_sync(MAPF_FULL_MASK, m2[0][w], 1, LW);
-            uint32_t az = __shfl_up_sync(MAPF_FULL_MASK, z[RPL - 1][w], 1, LW), bz = __shfl_down_sync(MAPF_FULL_MASK, z[0][w], 1, LW);
-            if (lane == 0) a1 = a2 = az = 0;
-            if (lane == LW - 1) b1 = b2 = bz = 0;
-#pragma unroll
-            for (int q = 0; q < RPL; ++q) {
-                auto left = [&](const uint32_t(&m)[RPL][RW]) {  // bit y <- bit y-1
-                    return w > 0 ? __funnelshift_l(m[q][w > 0 ? w - 1 : 0], m[q][w], 1) : m[q][w] << 1;
-                };
-                auto right = [&](const uint32_t(&m)[RPL][RW]) {  // bit y <- bit y+1
-                    return w < RW - 1 ? __funnelshift_r(m[q][w], m[q][w < RW - 1 ? w + 1 : w], 1) : m[q][w] >> 1;
-                };
-                const uint32_t c1 = m1[q][w], c2 = m2[q][w], cz = z[q][w];
-                const uint32_t u1 = q > 0 ? m1[q > 0 ? q - 1 : 0][w] : a1, u2 = q > 0 ? m2[q > 0 ? q - 1 : 0][w] : a2,
-                               uz = q > 0 ? z[q > 0 ? q - 1 : 0][w] : az;
-                const uint32_t d1 = q < RPL - 1 ? m1[q < RPL - 1 ? q + 1 : q][w] : b1, d2 = q < RPL - 1 ? m2[q < RPL - 1 ? q + 1 : q][w] : b2,
-                               dz = q < RPL - 1 ? z[q < RPL - 1 ? q + 1 : q][w] : bz;
-                pl[0][q][w] = closer(c1, c2, cz, u1, u2, uz);                       // neighbour x-1   environment.py:260
-                pl[1][q][w] = closer(c1, c2, cz, d1, d2, dz);                       // neighbour x+1   environment.py:264
-                pl[2][q][w] = closer(c1, c2, cz, left(m1), left(m2), left(z));      // neighbour y-1   environment.py:268
-                pl[3][q][w] = closer(c1, c2, cz, right(m1), right(m2), right(z));   // neighbour y+1   environment.py:272
-            }
+            auto left = [&](const uint32_t(&m)[RPL][RW]) {  // bit y <- bit y-1
+                return w > 0 ? __funnelshift_l(m[q][w > 0 ? w - 1 : 0], m[q][w], 1) : m[q][w] << 1;
+            };
+            auto right = [&](const uint32_t(&m)[RPL][RW]) {  // bit y <- bit y+1
+                return w < RW - 1 ? __funnelshift_r(m[q][w], m[q][w < RW - 1 ? w + 1 : w], 1) : m[q][w] >> 1;
+            };
+            const uint32_t c1 = S.m1[q][w], c2 = S.m2[q][w], cz = z[q][w];
+            const uint32_t u1 = q > 0 ? S.m1[q > 0 ? q - 1 : 0][w] : a1, u2 = q > 0 ? S.m2[q > 0 ? q - 1 : 0][w] : a2,
+                           uz = q > 0 ? z[q > 0 ? q - 1 : 0][w] : az;
+            const uint32_t d1 = q < RPL - 1 ? S.m1[q < RPL - 1 ? q + 1 : q][w] : b1, d2 = q < RPL - 1 ? S.m2[q < RPL - 1 ? q + 1 : q][w] : b2,
+                           dz = q < RPL - 1 ? z[q < RPL - 1 ? q + 1 : q][w] : bz;
+            pl[0][q][w] = closer(c1, c2, cz, u1, u2, uz);                             // neighbour x-1   environment.py:260
+            pl[1][q][w] = closer(c1, c2, cz, d1, d2, dz);                             // neighbour x+1   environment.py:264
+            pl[2][q][w] = closer(c1, c2, cz, left(S.m1), left(S.m2), left(z));        // neighbour y-1   environment.py:268
+            pl[3][q][w] = closer(c1, c2, cz, right(S.m1), right(S.m2), right(z));     // neighbour y+1   environment.py:272
         }
     }
-
-    // emit the overlapping 16x16 tiles (mapf_common.cuh): a map row is padded row pr = row + 4, which is
-    // row pr & 7 of tile row-block pr >> 3 and row (pr & 7) + 8 of the block above
     uint2 *nv = reinterpret_cast<uint2 *>(navi + ((size_t)e * d.N + a) * d.navi_agent_stride);
 #pragma unroll
     for (int q = 0; q < RPL; ++q) {
@@ -196,6 +173,65 @@ __device__ __forceinline__ void bfs_navi_warp(const EnvDims &d, const int e, con
             if (bx1 > 0) nv[((size_t)((bx1 - 1) * d.NB + by) << 4) + r1 + 8] = v;
         }
     }
+}
+
+// One search per agent group of the warp (the load / reset kernels): every wave is followed by a vote, int32 distances are
+// emitted on request (parity with search.compute_heuristics).
+template <int RW, int RPL, int APW>
+__device__ __forceinline__ void bfs_navi_warp(const EnvDims &d, const int e, const int a, const int i, const bool alive,
+                                              const uint32_t *__restrict__ obst, const uint8_t *__restrict__ goal,
+                                              uint32_t *__restrict__ navi, int32_t *__restrict__ dist_out)
+{
+    constexpr int LW = 32 / APW;
+    const int lane = (threadIdx.x & 31) % LW;
+    const uint32_t *ob = obst + (size_t)e * d.obst_stride;
+    const uchar2 gg = __ldcg(reinterpret_cast<const uchar2 *>(goal) + (size_t)e * d.N + a);
+    const int gx = gg.x, gy = gg.y;
+    BfsState<RW, RPL> S;
+    bfs_init<RW, RPL, APW>(d, ob, gx, gy, alive, S);
+
+    int32_t *dist = (dist_out && alive) ? dist_out + ((size_t)i * d.N + a) * d.L * d.L : nullptr;
+    if (dist_out) {
+        for (int q = 0; q < RPL; ++q) {
+            const int row = lane * RPL + q;
+            if (dist && row < d.L)
+                for (int y = 0; y < d.L; ++y) dist[row * d.L + y] = MAPF_DIST_UNREACHABLE;
+        }
+        __syncwarp();
+#pragma unroll
+        for (int q = 0; q < RPL; ++q)
+#pragma unroll
+            for (int w = 0; w < RW; ++w)
+                if (dist && S.fro[q][w]) dist[gx * d.L + gy] = 0;
+    }
+
+    auto wave = [&](auto selc, const int t) -> bool {
+        constexpr int sel = decltype(selc)::value;  // t mod 3
+        uint32_t nw[RPL][RW];
+        const uint32_t any = bfs_wave<RW, RPL, APW>(S, nw);
+        if (!__any_sync(MAPF_FULL_MASK, any != 0)) return false;
+        bfs_apply<RW, RPL, sel>(S, nw);
+        if (dist_out) {  // a kernel argument: the loop is compiled twice, the common one without any of this
+#pragma unroll
+            for (int q = 0; q < RPL; ++q)
+#pragma unroll
+                for (int w = 0; w < RW; ++w) {
+                    uint32_t x = dist ? nw[q][w] : 0u;
+                    while (x) {
+                        int b = __ffs(x) - 1;
+                        x &= x - 1;
+                        dist[(lane * RPL + q) * d.L + (32 * w + b - 4)] = t;
+                    }
+                }
+        }
+        return true;
+    };
+    for (int t = 1;; t += 3) {
+        if (!wave(std::integral_constant<int, 1>{}, t)) break;
+        if (!wave(std::integral_constant<int, 2>{}, t + 1)) break;
+        if (!wave(std::integral_constant<int, 0>{}, t + 2)) break;
+    }
+    bfs_emit<RW, RPL, APW>(d, ob, e, a, alive, S, navi);
 }
 
 }  // namespace

@@ -65,6 +65,8 @@ struct mapf_env {
     unsigned long long *ro_work;  // [0] next work item, [1] warps that have left; both 0 between launches
     uint32_t *ro_progress;        // [B] chunks of an environment finished inside the running launch
     uint32_t *ro_episode;         // [B] instances generated for the slot by in-launch episode handling
+    uint32_t *ro_prio;            // [1 + B] count + ids of the environments that hit the step cap inside the next launch
+    uint8_t *ro_prio_flag;        // [B]
     int ro_key, ro_per_sm;
     // episode handling inside mapf_env_rollout (mapf_env_set_autoreset); ar_max_steps == 0: off
     int ar_max_steps;
@@ -89,11 +91,17 @@ struct mapf_env {
     int hg_next;
     int checks_gen;
     cudaStream_t cap_stream;
-    // mapf_env_step_host_codes: completion flag in page-locked host memory (and its device alias), publication counter
-    volatile uint32_t *h_flag;
-    uint32_t *d_flag;
-    uint32_t *pub_counter;
-    uint32_t pub_seq;
+    // mapf_env_step_host_codes: a two-stage pipeline -- step kernel + result copy on an internal stream, observe kernel on
+    // the caller's stream reading a SNAPSHOT of the positions, so that step t+1 overlaps the observation stores of step t
+    cudaStream_t hp_stream;        // step kernel + result copies
+    cudaEvent_t hp_step[2];        // step t (kernel + copies) done
+    cudaEvent_t hp_obs[2];         // observe kernel of step t done (its position snapshot may be overwritten)
+    cudaEvent_t hp_in;             // what the caller queued before the first call of a run
+    cudaEvent_t hp_stepped;        // the step kernel of the current call is done (the observe kernel may start)
+    uint8_t *hp_pos[2];            // u8[B,N,2] position snapshots
+    uint8_t *hp_results;           // device staging: codes u8[BN] | pad 16 | steps i32[B] | done u8[B]
+    uint64_t hp_t;                 // calls since the pipeline was (re)started
+    int hp_active;                 // work of the pipeline may still be in flight (other entry points drain it first)
     int64_t arena_bytes;
 };
 
@@ -121,20 +129,12 @@ struct StepParams {
     int env_begin, env_end;  // the launch covers environments [env_begin, env_end) of the batch
 };
 
-// optional host publication of a step's results (see step_observe_kernel)
-struct StepPublish {
-    uint32_t *counter = nullptr;  // device: environments of the launch that have published
-    uint32_t *flag = nullptr;     // device alias of a page-locked host word: receives `seq` once every environment has published
-    uint32_t seq = 0;
-};
-
 // outputs of a step launch; rewards and codes are each optional
 struct StepOut {
     float *rewards = nullptr;   // f32[B,N]
     uint8_t *codes = nullptr;   // u8[B,N] MAPF_RCODE_*
     uint8_t *done = nullptr;    // u8[B]
     int32_t *steps = nullptr;   // i32[B] optional
-    StepPublish pub;
 };
 
 struct mapf_env;

@@ -324,7 +324,10 @@ __device__ __forceinline__ void env_step_gather(const StepParams &p, const int e
             for (int k = 0; k < K; ++k) {
                 const int a = k * 32 + lane;
                 if (valid[k]) {
-                    reinterpret_cast<uchar2 *>(p.pos)[(size_t)e * N + a] = make_uchar2((unsigned char)px[k], (unsigned char)py[k]);
+                    const uchar2 np = make_uchar2((unsigned char)px[k], (unsigned char)py[k]);
+                    reinterpret_cast<uchar2 *>(p.pos)[(size_t)e * N + a] = np;
+                    if constexpr (!DO_OBS)
+                        if (p.pos_out) reinterpret_cast<uchar2 *>(p.pos_out)[(size_t)e * N + a] = np;  // snapshot for a later observe
                     const int c = reset_step ? RC_RESET : (done ? RC_FINISH : code[k]);
                     if (p.rewards) p.rewards[(size_t)e * N + a] = reward_of(p, c);
                     if (p.codes) p.codes[(size_t)e * N + a] = (uint8_t)c;

@@ -17,13 +17,9 @@
 namespace {
 
 // ---- K1+K2: every warp steps an env, then expands and stores its own observation block.
-// Host publication (mapf_env_step_host_codes): when p.publish_flag is set, reward codes / done / steps point at page-locked
-// HOST memory; every warp makes its results visible system-wide as soon as the conflict resolution is done, the last warp
-// of the launch then stores the step's sequence number into the host flag -- the caller polls that flag and returns while
-// the observation stores (the bulk of the kernel) are still draining.
 template <int RW, int K, bool DO_STEP, int WARPS, int MINB>
 __global__ void __launch_bounds__(WARPS * 32, MINB)
-step_observe_kernel(const StepParams p, const StepPublish pub)
+step_observe_kernel(const StepParams p)
 {
     extern __shared__ __align__(16) uint32_t smem[];
     const EnvDims &d = p.d;
@@ -51,28 +47,15 @@ step_observe_kernel(const StepParams p, const StepPublish pub)
         const int head = (int)(reinterpret_cast<uintptr_t>(obs_env) & 15);  // bytes before the 16-B boundary
         EnvRegs<K> r;
         env_step_gather<RW, K, DO_STEP>(p, e, lane, s_obst, s_agent, s_bits, s_tgt, s_cell, head, pol_keep, r);
-        if constexpr (DO_STEP) {
-            if (pub.flag) {
-                __threadfence_system();  // this lane's result stores (host memory) are performed system-wide
-                __syncwarp();
-                if (lane == 0) {
-                    const unsigned prev = atomicAdd(pub.counter, 1u);
-                    if (prev + 1 == (unsigned)(p.env_end - p.env_begin)) {  // every environment of the launch has published
-                        __threadfence_system();
-                        *pub.counter = 0;
-                        *reinterpret_cast<volatile uint32_t *>(pub.flag) = pub.seq;
-                    }
-                }
-            }
-        }
         expand_store_block(p, obs_env, head, env_bytes, s_bits, lane, obs_policy, pol_stream);
         __syncwarp();
         clear_agent_bits<RW, K>(s_agent, r);  // the agent bits this env set
     }
 }
 
-// ---- K1 alone: Environment.step without the observation.  mapf_env_step_host (mode 4) launches it ahead of the observe
-// kernel so that the device-to-host copies of rewards / done / steps run WHILE the observation is being written.
+// ---- K1 alone: Environment.step without the observation.  The host-buffer steps launch it ahead of the observe kernel so
+// that the device-to-host copies of the results run WHILE the observation is being written; with p.pos_out it also leaves a
+// snapshot of the new positions for that observe kernel, so the NEXT step may overwrite the positions meanwhile.
 template <int RW, int K>
 __global__ void __launch_bounds__(128)
 step_only_kernel(const StepParams p)
@@ -125,7 +108,7 @@ StepTuning &tuning()
 }
 
 template <int RW, int K, bool DO_STEP, int WARPS, int MINB>
-int launch_step_cfg(const mapf_env *env, StepParams &p, const StepPublish &pub, cudaStream_t st)
+int launch_step_cfg(const mapf_env *env, StepParams &p, cudaStream_t st)
 {
     auto kern = step_observe_kernel<RW, K, DO_STEP, WARPS, MINB>;
     const size_t smem = (size_t)p.warp_smem_words * 4 * WARPS;
@@ -140,13 +123,13 @@ int launch_step_cfg(const mapf_env *env, StepParams &p, const StepPublish &pub, 
         const int cap = env->num_sms * tuning().ctas_per_sm;
         if (grid > cap) grid = cap;
     }
-    kern<<<grid, WARPS * 32, smem, st>>>(p, pub);
+    kern<<<grid, WARPS * 32, smem, st>>>(p);
     MAPF_CUDA(cudaGetLastError());
     return MAPF_OK;
 }
 
 template <int RW, int K, bool DO_STEP>
-int launch_step_rwk(const mapf_env *env, StepParams &p, const StepPublish &pub, cudaStream_t st)
+int launch_step_rwk(const mapf_env *env, StepParams &p, cudaStream_t st)
 {
     if constexpr (RW == 2 && K == 1) {
         // CTA shape / register budget of the hot geometry (40x40, <= 32 agents), measured at 8192 x 32 (profiles/
@@ -158,9 +141,9 @@ int launch_step_rwk(const mapf_env *env, StepParams &p, const StepPublish &pub, 
         int v = tuning().variant;
         if (v == 1) v = (p.env_end - p.env_begin < env->d.B) ? 7 : 0;
         switch (v) {
-            case 0: return launch_step_cfg<RW, K, DO_STEP, 8, 5>(env, p, pub, st);
-            case 7: return launch_step_cfg<RW, K, DO_STEP, 8, 4>(env, p, pub, st);
-            case 8: return launch_step_cfg<RW, K, DO_STEP, 4, 8>(env, p, pub, st);
+            case 0: return launch_step_cfg<RW, K, DO_STEP, 8, 5>(env, p, st);
+            case 7: return launch_step_cfg<RW, K, DO_STEP, 8, 4>(env, p, st);
+            case 8: return launch_step_cfg<RW, K, DO_STEP, 4, 8>(env, p, st);
             default: break;  // 4: the general shape below
         }
     }
@@ -170,32 +153,32 @@ int launch_step_rwk(const mapf_env *env, StepParams &p, const StepPublish &pub, 
         // the rollout's sub-batch launches are no faster (52.8 vs 52.4 us per step; profiles/r1_rollout_cta_shapes.log)
         int v = tuning().variant;
         if (v == 1) v = (p.env_end - p.env_begin < env->d.B) ? 4 : 9;
-        if (v == 9) return launch_step_cfg<RW, K, DO_STEP, 4, 8>(env, p, pub, st);
+        if (v == 9) return launch_step_cfg<RW, K, DO_STEP, 4, 8>(env, p, st);
     }
-    return launch_step_cfg<RW, K, DO_STEP, 4, (K == 1 ? 12 : 1)>(env, p, pub, st);
+    return launch_step_cfg<RW, K, DO_STEP, 4, (K == 1 ? 12 : 1)>(env, p, st);
 }
 
 template <int RW, bool DO_STEP>
-int launch_step_rw(const mapf_env *env, StepParams &p, const StepPublish &pub, cudaStream_t st)
+int launch_step_rw(const mapf_env *env, StepParams &p, cudaStream_t st)
 {
     switch (env->d.K) {
-        case 1: return launch_step_rwk<RW, 1, DO_STEP>(env, p, pub, st);
-        case 2: return launch_step_rwk<RW, 2, DO_STEP>(env, p, pub, st);
-        case 3: return launch_step_rwk<RW, 3, DO_STEP>(env, p, pub, st);
-        case 4: return launch_step_rwk<RW, 4, DO_STEP>(env, p, pub, st);
+        case 1: return launch_step_rwk<RW, 1, DO_STEP>(env, p, st);
+        case 2: return launch_step_rwk<RW, 2, DO_STEP>(env, p, st);
+        case 3: return launch_step_rwk<RW, 3, DO_STEP>(env, p, st);
+        case 4: return launch_step_rwk<RW, 4, DO_STEP>(env, p, st);
     }
     mapf_set_error("unsupported agent count");
     return MAPF_EINVAL;
 }
 
 template <bool DO_STEP>
-int launch_step(const mapf_env *env, StepParams &p, const StepPublish &pub, cudaStream_t st)
+int launch_step(const mapf_env *env, StepParams &p, cudaStream_t st)
 {
     switch (env->d.RW) {
-        case 1: return launch_step_rw<1, DO_STEP>(env, p, pub, st);
-        case 2: return launch_step_rw<2, DO_STEP>(env, p, pub, st);
-        case 3: return launch_step_rw<3, DO_STEP>(env, p, pub, st);
-        case 4: return launch_step_rw<4, DO_STEP>(env, p, pub, st);
+        case 1: return launch_step_rw<1, DO_STEP>(env, p, st);
+        case 2: return launch_step_rw<2, DO_STEP>(env, p, st);
+        case 3: return launch_step_rw<3, DO_STEP>(env, p, st);
+        case 4: return launch_step_rw<4, DO_STEP>(env, p, st);
     }
     mapf_set_error("unsupported map size");
     return MAPF_EINVAL;
@@ -260,7 +243,7 @@ int mapf_launch_step(mapf_env *env, const uint8_t *d_actions, uint8_t *d_obs, co
     p.obs = d_obs;
     p.obs_rows = d_obs_rows;
     fill_out(p, out);
-    return launch_step<true>(env, p, out.pub, st);
+    return launch_step<true>(env, p, st);
 }
 
 template <int RW, int K>
@@ -289,13 +272,14 @@ int mapf_launch_step_range(mapf_env *env, int e0, int e1, const uint8_t *d_actio
     fill_out(p, out);
     p.env_begin = e0;
     p.env_end = e1;
-    return launch_step<true>(env, p, StepPublish{}, st);
+    return launch_step<true>(env, p, st);
 }
 
-int mapf_launch_step_only(mapf_env *env, const uint8_t *d_actions, const StepOut &out, cudaStream_t st)
+int mapf_launch_step_only(mapf_env *env, const uint8_t *d_actions, const StepOut &out, uint8_t *d_pos_snapshot, cudaStream_t st)
 {
     StepParams p = mapf_make_step_params(env);
     p.actions = d_actions;
+    p.pos_out = d_pos_snapshot;
     fill_out(p, out);
     switch (env->d.RW * 10 + env->d.K) {
         case 11: return launch_step_only_cfg<1, 1>(env, p, st);
@@ -319,11 +303,14 @@ int mapf_launch_step_only(mapf_env *env, const uint8_t *d_actions, const StepOut
     return MAPF_EINVAL;
 }
 
-int mapf_launch_observe(mapf_env *env, uint8_t *d_obs, const int64_t *d_obs_rows, uint8_t *d_pos, cudaStream_t st)
+// d_pos_src (optional): observe THESE positions (a snapshot left by mapf_launch_step_only) instead of the handle's
+int mapf_launch_observe(mapf_env *env, uint8_t *d_obs, const int64_t *d_obs_rows, uint8_t *d_pos, const uint8_t *d_pos_src,
+                        cudaStream_t st)
 {
     StepParams p = mapf_make_step_params(env);
+    if (d_pos_src) p.pos = const_cast<uint8_t *>(d_pos_src);
     p.obs = d_obs;
     p.obs_rows = d_obs_rows;
     p.pos_out = d_pos;
-    return launch_step<false>(env, p, StepPublish{}, st);
+    return launch_step<false>(env, p, st);
 }

@@ -192,7 +192,7 @@ def rollout_tuning():
     lib = _native.lib()
     yield lambda persistent=-1, warps_per_sm=-1, chunk=-1, store_mode=-1, stagger_ns=-1: \
         lib.mapf_debug_rollout_tuning(persistent, warps_per_sm, chunk, store_mode, stagger_ns)
-    lib.mapf_debug_rollout_tuning(1, 0, 0, 0, 4000)
+    lib.mapf_debug_rollout_tuning(1, 0, 0, 0, 1000)
 
 
 def _rollout_vs_twin(env, twin, acts, T, A, R, S, want_codes=False, oracle_envs=(0, 1)):
