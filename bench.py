@@ -495,10 +495,11 @@ def run_ours(args):
                               "ms_per_step": ms_single / K, "value": world * B * N * K / (ms_single * 1e-3),
                               "roofline_frac": ab * B * N / (ms_single * 1e-3 / K) / 1e9 / peak},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * N, "d2h_bytes_per_step": B * N + B * 5,
-                    "api": "mapf_env_step_host_codes on one of 16 page-locked action buffers: ONE fused step+observe kernel reads the "
-                           "actions in place over PCIe and stores u8 reward codes / done / steps straight into page-locked host "
-                           "memory; the call returns when the host flag is raised (results final), the observation stores drain on "
-                           "the stream into the device replay ring (north star); timed with a device synchronize at the end",
+                    "api": "mapf_env_step_host_codes on one of 16 page-locked action buffers, a two-stage pipeline: the step kernel reads "
+                           "the actions in place over PCIe and ONE DMA copy brings u8 reward codes / steps / done back (internal stream); "
+                           "the call returns when they are on the host, while the observe kernel writes the observation of a position "
+                           "snapshot into the device replay ring on the caller's stream (north star), overlapping the next call's "
+                           "step stage; timed with a device synchronize at the end",
                     "steps": e2e_steps, "repetitions": [r[0] for r in reps], "per_rank_s": e2e_times},
             "e2e_f32_rewards": {"value": e2e_f32_value, "unit": UNIT, "h2d_bytes_per_step": B * N, "d2h_bytes_per_step": B * N * 4 + B * 5,
                                 "api": "mapf_env_step_host (fp32 rewards, step kernel -> observe kernel || D2H copies, CUDA graph, stream sync)"},

@@ -51,6 +51,19 @@ def _worker(rank, world, port, per_gpu, q):
         dist.all_gather_object(gathered, (maps, agents, goals))
         t_max = sharding.max_over_ranks(10.0 + rank)
         t_sum = sharding.sum_over_ranks(float(per_gpu))
+        assert sharding.gather_floats(3.0 + rank) == [3.0 + r for r in range(world)]
+        # the learner's gradient averaging (the package's only collective): one all-reduce of the flattened gradients
+        import torch
+        from mapf_rl_b200.learner import BatchedLearner
+        torch.manual_seed(0)
+        model = torch.nn.Sequential(torch.nn.Linear(4, 3), torch.nn.Linear(3, 2))
+        for k, p in enumerate(model.parameters()):
+            p.grad = torch.full_like(p, float(rank + 1) * (k + 1))
+        shim = type("L", (), {"allreduce": True, "model": model})()
+        BatchedLearner._allreduce_grads(shim)
+        mean = sum(range(1, world + 1)) / world
+        for k, p in enumerate(model.parameters()):
+            assert torch.allclose(p.grad, torch.full_like(p, mean * (k + 1)))
         dist.barrier()
         if rank == 0:
             q.put((gathered, t_max, t_sum))
