@@ -245,9 +245,16 @@ rollout_kernel(const __grid_constant__ StepParams p0, const __grid_constant__ Ro
         EnvRegs<K> regs;
         load_env_state<RW, K>(p0, e, lane, s_obst, regs);
         int sa = t0 % r.action_slots, so = t0 % r.obs_slots, sr = t0 % r.out_slots;
+#pragma unroll
+        for (int k = 0; k < K; ++k) {  // the first step's actions; every later step's are requested one step ahead
+            const int a = k * 32 + lane;
+            regs.act_next[k] = a < N ? __ldg(r.actions + (size_t)sa * BN + (size_t)e * N + a) : 0;
+        }
         for (int t = t0; t < t1; ++t) {
             StepParams p = p0;
             p.actions = r.actions + (size_t)sa * BN;
+            const int sa_next = sa + 1 == r.action_slots ? 0 : sa + 1;
+            const uint8_t *next_actions = t + 1 < t1 ? r.actions + (size_t)sa_next * BN : nullptr;
             p.rewards = r.rewards ? r.rewards + (size_t)sr * BN : nullptr;
             p.codes = r.codes ? r.codes + (size_t)sr * BN : nullptr;
             p.done = r.done + (size_t)sr * d.B;
@@ -261,12 +268,19 @@ rollout_kernel(const __grid_constant__ StepParams p0, const __grid_constant__ Ro
                 const int st = __shfl_sync(MAPF_FULL_MASK, regs.step, 0);
                 if (regs.finished || st >= r.max_steps) {
                     regenerate_env<RW>(p0, r, e);
-                    load_env_state<RW, K>(p0, e, lane, s_obst, regs);
+                    {
+                        int keep[K];   // load_env_state starts a fresh EnvRegs; the prefetched actions stay
+#pragma unroll
+                        for (int k = 0; k < K; ++k) keep[k] = regs.act_next[k];
+                        load_env_state<RW, K>(p0, e, lane, s_obst, regs);
+#pragma unroll
+                        for (int k = 0; k < K; ++k) regs.act_next[k] = keep[k];
+                    }
                     reset_step = true;
                 }
             }
             env_step_gather<RW, K, true, true, true>(p, e, lane, s_obst, s_agent, s_bits, s_tgt, s_cell, head, pol_keep, regs, nullptr,
-                                                     s_tiles, reset_step);
+                                                     s_tiles, reset_step, next_actions);
             if (r.store_mode == 1 && head == 0 && (env_bytes & 15) == 0) {
                 // bulk form: bits -> bool bytes into the staging block, then one TMA store of the whole block
                 if (bulk_used) {

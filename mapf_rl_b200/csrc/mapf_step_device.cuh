@@ -115,6 +115,7 @@ struct EnvRegs {
     // carried from step to step by the persistent rollout kernel only:
     int gx[K], gy[K];  // goals
     int tile[K];       // navi tile (x >> 3) * NB + (y >> 3) held in the agent's shared-memory tile slot, -1 = none
+    int act_next[K];   // the action of the NEXT step, requested one step ahead (the only global load of a resident step)
     int step;          // step counter
     bool finished;     // all agents stood on their goals after the last step (environment.py:415)
 };
@@ -128,13 +129,14 @@ struct EnvRegs {
 // one load (the action); the heuristic rows come from the agent's tile slot in shared memory (`s_tiles`), refilled with
 // cp.async only when the agent has moved to another tile (once in ~12 steps).  `reset_step`: the environment has just
 // been re-generated -- nobody moves, rewards are 0, done is 0 and the step counter stays 0 (the call emits the new
-// episode's first observation).
+// episode's first observation).  Actions are software-pipelined: out.act_next holds this step's actions (the kernel loads
+// the first step's), `next_actions` (NULL on the last step of an item) is where the next step's are requested from.
 template <int RW, int K, bool DO_STEP, bool DO_OBS = true, bool RESIDENT = false>
 __device__ __forceinline__ void env_step_gather(const StepParams &p, const int e, const int lane, uint32_t *s_obst,
                                                 uint32_t *s_agent, uint32_t *s_bits, uint16_t *s_tgt, uint16_t *s_cell,
                                                 const int head, const uint64_t pol_keep, EnvRegs<K> &out,
                                                 const uint8_t *s_act = nullptr, uint64_t *s_tiles = nullptr,
-                                                const bool reset_step = false)
+                                                const bool reset_step = false, const uint8_t *next_actions = nullptr)
 {
     constexpr int RWS = RW + 1;
     const EnvDims &d = p.d;
@@ -169,7 +171,10 @@ __device__ __forceinline__ void env_step_gather(const StepParams &p, const int e
                 if constexpr (DO_STEP) {
                     gx[k] = out.gx[k];
                     gy[k] = out.gy[k];
-                    if (valid[k] && !reset_step) act[k] = __ldg(p.actions + (size_t)e * N + a);
+                    // this step's action was requested during the previous step (the load's ~1 us of latency used to be the
+                    // first thing every step waited for: 9 % of the kernel's stall samples); request the next one now
+                    if (!reset_step) act[k] = out.act_next[k];
+                    if (valid[k] && next_actions) out.act_next[k] = __ldg(next_actions + (size_t)e * N + a);
                 }
             } else if (valid[k]) {
                 const uchar2 pp = reinterpret_cast<const uchar2 *>(p.pos)[(size_t)e * N + a];
