@@ -205,12 +205,15 @@ int mapf_env_rollout_plan(mapf_env *env, int32_t T, int32_t action_slots, int32_
 int mapf_env_step_host(mapf_env *env, const uint8_t *h_actions, uint8_t *h_obs, float *h_rewards,
                        uint8_t *h_done, int32_t *h_steps, uint8_t *d_obs_opt, void *stream);
 
-/* The throughput form of the host-buffer step: reward CODES (u8[B, N], MAPF_RCODE_*) instead of fp32 rewards, ONE fused
- * kernel, no DMA nodes.  The kernel reads the page-locked actions in place, and every environment stores its codes / done /
- * steps straight into the (page-locked) host buffers as soon as its conflict resolution is done; the last one raises a
- * host flag.  The call returns when the flag is up: h_codes / h_done / h_steps are final, while the observation stores
- * into d_obs (required, device memory) are still draining on `stream` -- they are ordered before anything queued on
- * `stream` afterwards, including the next step.  Pageable host buffers are staged as above. */
+/* The throughput form of the host-buffer step: reward CODES (u8[B, N], MAPF_RCODE_*) instead of fp32 rewards, run as a
+ * two-stage pipeline.  Stage 1 (an internal stream): the step kernel reads the page-locked actions in place over PCIe and
+ * leaves codes / steps / done in a device staging block plus a SNAPSHOT of the new positions; one DMA copy brings the
+ * staging block back when h_steps == h_codes + align16(B*N) and h_done == h_steps + B (three copies otherwise).  Stage 2
+ * (the caller's `stream`): the observe kernel writes the observation of that snapshot into d_obs (required, device memory).
+ * The call returns when stage 1 is done -- h_codes / h_done / h_steps are final -- while stage 2 may still be running; it is
+ * ordered before anything queued on `stream` afterwards, and the NEXT call's stage 1 overlaps it (it may overwrite the
+ * positions, the snapshot is double-buffered).  Any other entry point on the handle first waits for the pipeline to drain.
+ * Pageable host buffers are staged through the handle's own pinned area. */
 int mapf_env_step_host_codes(mapf_env *env, const uint8_t *h_actions, uint8_t *h_codes, uint8_t *h_done, int32_t *h_steps,
                              uint8_t *d_obs, void *stream);
 
