@@ -327,11 +327,26 @@ class BatchedEnvironment:
         are final, while the observation (device tensor `device_obs`, required) is still being written on the current
         stream.  Returns (codes uint8[B,N], done uint8[B], steps int32[B]) numpy VIEWS of page-locked buffers owned by this
         object (overwritten by the next call); rewards = reward_table[codes], see `reward_table`."""
-        hb = self._host_buffers(False)
+        hb = getattr(self, "_hb", None) or self._host_buffers(False)
         pc, pd, ps = hb["codes_ptrs"]
-        pa = self._host_actions_ptr(actions, hb, hb["ptrs"][0])
-        _native.check(self._lib.mapf_env_step_host_codes(self._h, pa, pc, pd, ps, C.c_void_p(device_obs.data_ptr()),
-                                                        self._stream()))
+        fast = hb.get("_fast")
+        if fast is None:
+            torch = _torch()
+            fast = hb["_fast"] = (self._lib.mapf_env_step_host_codes, torch.Tensor, torch.cuda.current_stream)
+        fn, tensor_t, cur = fast
+        if type(actions) is tensor_t and actions.dtype is hb["actions"].dtype and actions.device.type == "cpu":
+            # hot path of an actor that rotates over its own uint8 CPU tensors: shape / contiguity are checked once per buffer
+            key = actions.data_ptr()
+            seen = hb.setdefault("_seen", set())
+            if key not in seen:
+                assert actions.is_contiguous() and tuple(actions.shape) == (self.num_envs, self.num_agents), "actions number"
+                if len(seen) > 256:
+                    seen.clear()
+                seen.add(key)
+            pa = key
+        else:
+            pa = self._host_actions_ptr(actions, hb, hb["ptrs"][0])
+        _native.check(fn(self._h, pa, pc, pd, ps, device_obs.data_ptr(), cur(self.device).cuda_stream))
         return hb["codes_np"], hb["cdone_np"], hb["csteps_np"]
 
     @property

@@ -19,6 +19,8 @@ int mapf_launch_step_range(mapf_env *, int, int, const uint8_t *, uint8_t *, con
 int mapf_launch_rollout(mapf_env *, int, int, int, const uint8_t *, int, uint8_t *, int, const StepOut &, int, cudaStream_t);
 bool mapf_rollout_supported(const mapf_env *);
 void mapf_set_rollout_tuning(int, int, int, int);
+void mapf_set_rollout_pregen(int);
+int &rollout_pregen_ref();
 void mapf_set_step_tuning(int, int, int);
 int mapf_step_tuning_generation();
 int mapf_launch_unpack(mapf_env *, uint8_t *, uint8_t *, cudaStream_t);
@@ -189,14 +191,18 @@ int mapf_env_create(const mapf_env_config *cfg, mapf_env **out)
     if (rc == MAPF_OK) rc = dev_alloc(&env->navi, BN * d.navi_agent_stride, &total);
     if (rc == MAPF_OK) rc = dev_alloc(&env->steps, (size_t)d.B, &total);
     if (rc == MAPF_OK) rc = dev_alloc(&env->err, 1, &total);
-    if (rc == MAPF_OK) rc = dev_alloc(&env->ro_work, 2, &total);
+    if (rc == MAPF_OK) rc = dev_alloc(&env->navi_sel, (size_t)d.B, &total);
+    if (rc == MAPF_OK) rc = dev_alloc(&env->pg_flag, (size_t)d.B, &total);
+    if (rc == MAPF_OK) rc = dev_alloc(&env->ro_work, 4, &total);
     if (rc == MAPF_OK) rc = dev_alloc(&env->ro_progress, (size_t)d.B, &total);
     if (rc == MAPF_OK) rc = dev_alloc(&env->ro_episode, (size_t)d.B, &total);
     if (rc == MAPF_OK) rc = dev_alloc(&env->ro_prio, (size_t)d.B + 1, &total);
     if (rc == MAPF_OK) rc = dev_alloc(&env->ro_prio_flag, (size_t)d.B, &total);
     if (rc == MAPF_OK) {
         cudaError_t e2 = cudaMemset(env->obst, 0, (size_t)d.B * d.obst_stride * 4);
-        if (e2 == cudaSuccess) e2 = cudaMemset(env->ro_work, 0, 16);
+        if (e2 == cudaSuccess) e2 = cudaMemset(env->ro_work, 0, 32);
+        if (e2 == cudaSuccess) e2 = cudaMemset(env->navi_sel, 0, (size_t)d.B);
+        if (e2 == cudaSuccess) e2 = cudaMemset(env->pg_flag, 0, (size_t)d.B);
         if (e2 == cudaSuccess) e2 = cudaMemset(env->ro_progress, 0, (size_t)d.B * 4);
         if (e2 == cudaSuccess) e2 = cudaMemset(env->ro_episode, 0, (size_t)d.B * 4);
         if (e2 == cudaSuccess) e2 = cudaMemset(env->pos, 0, BN * 2);
@@ -224,6 +230,13 @@ int mapf_env_destroy(mapf_env *env)
     cudaFree(env->pos);
     cudaFree(env->goal);
     cudaFree(env->navi);
+    cudaFree(env->navi_alt);
+    cudaFree(env->navi_sel);
+    cudaFree(env->pg_obst);
+    cudaFree(env->pg_pos);
+    cudaFree(env->pg_goal);
+    cudaFree(env->pg_steps);
+    cudaFree(env->pg_flag);
     cudaFree(env->steps);
     cudaFree(env->err);
     cudaFree(env->ro_work);
@@ -605,6 +618,29 @@ int mapf_env_set_autoreset(mapf_env *env, int32_t max_steps, uint64_t seed, uint
     env->ar_seed = seed, env->ar_offset = env_offset, env->ar_stride = stride ? stride : (uint64_t)env->d.B;
     env->ar_density = density;
     MAPF_CUDA(cudaMemsetAsync(env->ro_episode, 0, (size_t)env->d.B * 4, static_cast<cudaStream_t>(stream)));
+    MAPF_CUDA(cudaMemsetAsync(env->pg_flag, 0, (size_t)env->d.B, static_cast<cudaStream_t>(stream)));
+    if (max_steps > 0 && !env->navi_alt) {
+        // the second heuristic-map buffer and the staging of pre-generated instances (mapf_common.cuh).  Without the memory
+        // for them episodes are still handled, by re-generating inside the rollout kernel.
+        const EnvDims &d = env->d;
+        const size_t BN = (size_t)d.B * d.N;
+        int64_t total = 0;
+        int rc = dev_alloc(&env->navi_alt, BN * d.navi_agent_stride, &total);
+        if (rc == MAPF_OK) rc = dev_alloc(&env->pg_obst, (size_t)d.B * d.obst_stride, &total);
+        if (rc == MAPF_OK) rc = dev_alloc(&env->pg_pos, BN * 2, &total);
+        if (rc == MAPF_OK) rc = dev_alloc(&env->pg_goal, BN * 2, &total);
+        if (rc == MAPF_OK) rc = dev_alloc(&env->pg_steps, (size_t)d.B, &total);
+        if (rc == MAPF_OK) {
+            // border rows / columns of a staged bitmap are zero like the live one's (the generator writes map rows only)
+            MAPF_CUDA(cudaMemsetAsync(env->pg_obst, 0, (size_t)d.B * d.obst_stride * 4, static_cast<cudaStream_t>(stream)));
+            MAPF_CUDA(cudaMemsetAsync(env->navi_alt, 0, BN * d.navi_agent_stride * 4, static_cast<cudaStream_t>(stream)));
+            env->arena_bytes += total;
+        } else {
+            cudaGetLastError();
+            cudaFree(env->navi_alt), cudaFree(env->pg_obst), cudaFree(env->pg_pos), cudaFree(env->pg_goal), cudaFree(env->pg_steps);
+            env->navi_alt = nullptr, env->pg_obst = nullptr, env->pg_pos = env->pg_goal = nullptr, env->pg_steps = nullptr;
+        }
+    }
     return MAPF_OK;
 }
 
@@ -805,8 +841,8 @@ int mapf_env_step_host_codes(mapf_env *env, const uint8_t *h_actions, uint8_t *h
     const int slot = (int)(env->hp_t & 1);
     // the observe kernel of two calls ago has read the snapshot this step overwrites
     if (env->hp_t >= 2) MAPF_CUDA(cudaStreamWaitEvent(env->hp_stream, env->hp_obs[slot], 0));
-    // where the kernel writes its results: the caller's page-locked buffers (or the pinned staging area) in place, or the
-    // device staging block
+    // where the kernel writes its results: the device staging block (default), or -- MAPF_HOSTCODES_MODE=0 -- the caller's
+    // page-locked buffers / the pinned staging area in place
     uint8_t *codes_alias = nullptr, *done_alias = nullptr;
     int32_t *steps_alias = nullptr;
     bool out_direct = false;
@@ -818,8 +854,6 @@ int mapf_env_step_host_codes(mapf_env *env, const uint8_t *h_actions, uint8_t *h
             codes_alias = host_device_alias(pin_res), done_alias = host_device_alias(pin_res + off_done);
             steps_alias = reinterpret_cast<int32_t *>(host_device_alias(pin_res + off_steps));
         }
-    } else {
-        out_direct = host_is_pinned(h_codes) && host_is_pinned(h_done) && (!h_steps || host_is_pinned(h_steps));
     }
     const bool zero_copy = copy_mode == 0 && codes_alias && done_alias && (steps_alias || (out_direct && !h_steps));
     StepOut o;
@@ -852,6 +886,8 @@ int mapf_env_step_host_codes(mapf_env *env, const uint8_t *h_actions, uint8_t *h
     if (rc != MAPF_OK) return rc;
     MAPF_CUDA(cudaEventRecord(env->hp_obs[slot], st));
     if (!zero_copy) {
+        // (queried while the step kernel is already running: off the critical path)
+        out_direct = host_is_pinned(h_codes) && host_is_pinned(h_done) && (!h_steps || host_is_pinned(h_steps));
         const bool contiguous = out_direct && h_steps && reinterpret_cast<uint8_t *>(h_steps) == h_codes + off_steps && h_done == h_codes + off_done;
         if (contiguous) {
             MAPF_CUDA(cudaMemcpyAsync(h_codes, env->hp_results, res_bytes, cudaMemcpyDeviceToHost, env->hp_stream));
@@ -886,6 +922,12 @@ int mapf_debug_rollout_tuning(int32_t persistent, int32_t warps_per_sm, int32_t 
     if (persistent >= 0) rollout_persistent_ref() = persistent;
     mapf_set_rollout_tuning(warps_per_sm, chunk, store_mode, stagger_ns);
     return MAPF_OK;
+}
+
+int mapf_debug_rollout_pregen(int32_t on)
+{
+    if (on >= 0) mapf_set_rollout_pregen(on);
+    return rollout_pregen_ref();
 }
 
 int mapf_debug_step_host_mode(int32_t mode)

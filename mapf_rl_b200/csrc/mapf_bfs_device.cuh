@@ -59,7 +59,10 @@ __device__ __forceinline__ void bfs_init(const EnvDims &d, const uint32_t *ob, c
 }
 
 // One wave: nw = (frontier shifted to the four neighbours) & free-and-unvisited; returns the OR of this lane's words.
-template <int RW, int RPL, int APW>
+// WRAP: the group's last row is past the map (L < LW * RPL), so the neighbour rows can come from a rotating shuffle with
+// nothing to zero at the group's ends -- the first lane receives the last lane's (empty) last row, and what the last lane
+// receives lands on that empty row, where free-and-unvisited is 0.
+template <int RW, int RPL, int APW, bool WRAP>
 __device__ __forceinline__ uint32_t bfs_wave(const BfsState<RW, RPL> &S, uint32_t (&nw)[RPL][RW])
 {
     constexpr int LW = 32 / APW;
@@ -68,10 +71,16 @@ __device__ __forceinline__ uint32_t bfs_wave(const BfsState<RW, RPL> &S, uint32_
 #pragma unroll
     for (int w = 0; w < RW; ++w) {
         // rows of the neighbouring lanes that touch this lane's block
-        uint32_t above = __shfl_up_sync(MAPF_FULL_MASK, S.fro[RPL - 1][w], 1, LW);
-        uint32_t below = __shfl_down_sync(MAPF_FULL_MASK, S.fro[0][w], 1, LW);
-        if (lane == 0) above = 0;
-        if (lane == LW - 1) below = 0;
+        uint32_t above, below;
+        if constexpr (WRAP) {
+            above = __shfl_sync(MAPF_FULL_MASK, S.fro[RPL - 1][w], (lane + LW - 1) & (LW - 1), LW);
+            below = __shfl_sync(MAPF_FULL_MASK, S.fro[0][w], (lane + 1) & (LW - 1), LW);
+        } else {
+            above = __shfl_up_sync(MAPF_FULL_MASK, S.fro[RPL - 1][w], 1, LW);
+            below = __shfl_down_sync(MAPF_FULL_MASK, S.fro[0][w], 1, LW);
+            if (lane == 0) above = 0;
+            if (lane == LW - 1) below = 0;
+        }
 #pragma unroll
         for (int q = 0; q < RPL; ++q) {
             const uint32_t f = S.fro[q][w];
@@ -175,12 +184,14 @@ __device__ __forceinline__ void bfs_emit(const EnvDims &d, const uint32_t *ob, c
     }
 }
 
-// One search per agent group of the warp (the load / reset kernels): every wave is followed by a vote, int32 distances are
-// emitted on request (parity with search.compute_heuristics).
-template <int RW, int RPL, int APW>
-__device__ __forceinline__ void bfs_navi_warp(const EnvDims &d, const int e, const int a, const int i, const bool alive,
-                                              const uint32_t *__restrict__ obst, const uint8_t *__restrict__ goal,
-                                              uint32_t *__restrict__ navi, int32_t *__restrict__ dist_out)
+// One search per agent group of the warp.  The waves run three at a time (one per residue) and the warp votes on the third
+// only: a wave that finds nothing is followed by waves that find nothing, so at most two idle waves are run at the end.
+// DIST: int32 distances are emitted too (parity with search.compute_heuristics) -- a separate instantiation, so the common
+// loop carries none of it.
+template <int RW, int RPL, int APW, bool WRAP, bool DIST>
+__device__ __forceinline__ void bfs_navi_search(const EnvDims &d, const int e, const int a, const int i, const bool alive,
+                                                const uint32_t *__restrict__ obst, const uint8_t *__restrict__ goal,
+                                                uint32_t *__restrict__ navi, int32_t *__restrict__ dist_out)
 {
     constexpr int LW = 32 / APW;
     const int lane = (threadIdx.x & 31) % LW;
@@ -190,8 +201,9 @@ __device__ __forceinline__ void bfs_navi_warp(const EnvDims &d, const int e, con
     BfsState<RW, RPL> S;
     bfs_init<RW, RPL, APW>(d, ob, gx, gy, alive, S);
 
-    int32_t *dist = (dist_out && alive) ? dist_out + ((size_t)i * d.N + a) * d.L * d.L : nullptr;
-    if (dist_out) {
+    int32_t *dist = nullptr;
+    if constexpr (DIST) {
+        dist = alive ? dist_out + ((size_t)i * d.N + a) * d.L * d.L : nullptr;
         for (int q = 0; q < RPL; ++q) {
             const int row = lane * RPL + q;
             if (dist && row < d.L)
@@ -205,13 +217,12 @@ __device__ __forceinline__ void bfs_navi_warp(const EnvDims &d, const int e, con
                 if (dist && S.fro[q][w]) dist[gx * d.L + gy] = 0;
     }
 
-    auto wave = [&](auto selc, const int t) -> bool {
+    auto wave = [&](auto selc, const int t) -> uint32_t {
         constexpr int sel = decltype(selc)::value;  // t mod 3
         uint32_t nw[RPL][RW];
-        const uint32_t any = bfs_wave<RW, RPL, APW>(S, nw);
-        if (!__any_sync(MAPF_FULL_MASK, any != 0)) return false;
+        const uint32_t any = bfs_wave<RW, RPL, APW, WRAP>(S, nw);
         bfs_apply<RW, RPL, sel>(S, nw);
-        if (dist_out) {  // a kernel argument: the loop is compiled twice, the common one without any of this
+        if constexpr (DIST) {
 #pragma unroll
             for (int q = 0; q < RPL; ++q)
 #pragma unroll
@@ -224,14 +235,27 @@ __device__ __forceinline__ void bfs_navi_warp(const EnvDims &d, const int e, con
                     }
                 }
         }
-        return true;
+        return any;
     };
     for (int t = 1;; t += 3) {
-        if (!wave(std::integral_constant<int, 1>{}, t)) break;
-        if (!wave(std::integral_constant<int, 2>{}, t + 1)) break;
-        if (!wave(std::integral_constant<int, 0>{}, t + 2)) break;
+        wave(std::integral_constant<int, 1>{}, t);
+        wave(std::integral_constant<int, 2>{}, t + 1);
+        const uint32_t any = wave(std::integral_constant<int, 0>{}, t + 2);
+        if (!__any_sync(MAPF_FULL_MASK, any != 0)) break;
     }
     bfs_emit<RW, RPL, APW>(d, ob, e, a, alive, S, navi);
+}
+
+// All 32 lanes call together; picks the instantiation (uniform branches: L and dist_out are launch-wide).
+template <int RW, int RPL, int APW>
+__device__ __forceinline__ void bfs_navi_warp(const EnvDims &d, const int e, const int a, const int i, const bool alive,
+                                              const uint32_t *__restrict__ obst, const uint8_t *__restrict__ goal,
+                                              uint32_t *__restrict__ navi, int32_t *__restrict__ dist_out)
+{
+    constexpr int LW = 32 / APW;
+    if (dist_out) bfs_navi_search<RW, RPL, APW, false, true>(d, e, a, i, alive, obst, goal, navi, dist_out);
+    else if (d.L < LW * RPL) bfs_navi_search<RW, RPL, APW, true, false>(d, e, a, i, alive, obst, goal, navi, nullptr);
+    else bfs_navi_search<RW, RPL, APW, false, false>(d, e, a, i, alive, obst, goal, navi, nullptr);
 }
 
 }  // namespace

@@ -107,7 +107,7 @@ __global__ void __launch_bounds__(kBfsWarps * 32, RW * RPL <= 9 ? 8 : 1)  // <= 
                                                                           // wherever that does not spill
 bfs_navi_kernel(EnvDims d, const int32_t *__restrict__ env_ids, const uint8_t *__restrict__ env_mask, int n,
                 const uint32_t *__restrict__ obst, const uint8_t *__restrict__ goal, uint32_t *__restrict__ navi,
-                int32_t *__restrict__ dist_out)
+                uint32_t *__restrict__ navi_alt, const uint8_t *__restrict__ navi_sel, int32_t *__restrict__ dist_out)
 {
     constexpr int LW = 32 / APW;
     const int g = (blockIdx.x * kBfsWarps + (threadIdx.x >> 5)) * APW + lane_id() / LW;
@@ -117,7 +117,36 @@ bfs_navi_kernel(EnvDims d, const int32_t *__restrict__ env_ids, const uint8_t *_
     if (e < 0 || e >= d.B) alive = false, e = 0;           // bad slot id: latched by pack_load_kernel
     if (alive && env_mask && !env_mask[e]) alive = false;  // masked re-computation after a device-side reset
     if (!__any_sync(MAPF_FULL_MASK, alive)) return;
-    bfs_navi_warp<RW, RPL, APW>(d, e, a, i, alive, obst, goal, navi, dist_out);
+    // the slot's live buffer (mapf_common.cuh)
+    uint32_t *nv = (navi_alt && navi_sel[e]) ? navi_alt : navi;
+    bfs_navi_warp<RW, RPL, APW>(d, e, a, i, alive, obst, goal, nv, dist_out);
+}
+
+// The heuristic maps of the pre-generated NEXT instances of the listed slots (episode handling of mapf_env_rollout): reads
+// the staged obstacle bitmaps / goals, writes the buffer the slot's live instance does not use.  The list's length is only
+// known on the device, so a fixed grid claims (slot, agent group) items from a counter.
+template <int RW, int RPL, int APW>
+__global__ void __launch_bounds__(kBfsWarps * 32, RW * RPL <= 9 ? 8 : 1)
+pregen_bfs_kernel(EnvDims d, const uint32_t *__restrict__ list, unsigned long long *__restrict__ counter,
+                  const uint32_t *__restrict__ pg_obst, const uint8_t *__restrict__ pg_goal, uint32_t *__restrict__ navi,
+                  uint32_t *__restrict__ navi_alt, const uint8_t *__restrict__ navi_sel)
+{
+    constexpr int LW = 32 / APW;
+    const int lane = lane_id();
+    const unsigned groups = (unsigned)(d.N + APW - 1) / APW;
+    const unsigned long long items = (unsigned long long)list[0] * groups;
+    for (;;) {
+        unsigned long long it = 0;
+        if (lane == 0) it = atomicAdd(counter, 1ull);
+        it = __shfl_sync(MAPF_FULL_MASK, it, 0);
+        if (it >= items) break;
+        const unsigned i = (unsigned)(it / groups);
+        const int a = (int)(it - (unsigned long long)i * groups) * APW + lane / LW;
+        const int e = (int)list[1 + i];
+        const bool alive = a < d.N;
+        uint32_t *nv = navi_sel[e] ? navi : navi_alt;
+        bfs_navi_warp<RW, RPL, APW>(d, e, alive ? a : 0, 0, alive, pg_obst, pg_goal, nv, nullptr);
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -193,7 +222,8 @@ __global__ void unpack_map_kernel(EnvDims d, const uint32_t *__restrict__ obst, 
     map_out[idx] = (w >> ((y + 4) & 31)) & 1u;
 }
 
-__global__ void unpack_navi_kernel(EnvDims d, const uint32_t *__restrict__ navi, uint8_t *__restrict__ navi_out)
+__global__ void unpack_navi_kernel(EnvDims d, const uint32_t *__restrict__ navi, const uint32_t *__restrict__ navi_alt,
+                                   const uint8_t *__restrict__ navi_sel, uint8_t *__restrict__ navi_out)
 {
     size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     size_t total = (size_t)d.B * d.N * 4 * d.L * d.L;
@@ -204,7 +234,8 @@ __global__ void unpack_navi_kernel(EnvDims d, const uint32_t *__restrict__ navi,
     size_t ea = idx / ((size_t)4 * d.L * d.L);
     const int pr = x + 4, pc = y + 4;
     const int bx = min(pr >> 3, d.NB - 1), by = min(pc >> 3, d.NB - 1);
-    const uint2 v = reinterpret_cast<const uint2 *>(navi + ea * d.navi_agent_stride)[((size_t)(bx * d.NB + by) << 4) + (pr - 8 * bx)];
+    const uint32_t *live = (navi_alt && navi_sel[ea / d.N]) ? navi_alt : navi;
+    const uint2 v = reinterpret_cast<const uint2 *>(live + ea * d.navi_agent_stride)[((size_t)(bx * d.NB + by) << 4) + (pr - 8 * bx)];
     const uint32_t half = k < 2 ? v.x : v.y;
     navi_out[idx] = (half >> (16 * (k & 1) + (pc - 8 * by))) & 1u;
 }
@@ -230,35 +261,52 @@ int mapf_launch_validate_state(mapf_env *env, const int32_t *d_env_ids, int n, c
     return MAPF_OK;
 }
 
+// pregen = true: pregen_bfs_kernel over the list in env->ro_prio (ids / mask / n / dist unused)
 template <int RW>
-static int launch_bfs_rw(mapf_env *env, const int32_t *ids, const uint8_t *mask, int n, int32_t *dist, cudaStream_t st)
+static int launch_bfs_rw(mapf_env *env, const int32_t *ids, const uint8_t *mask, int n, int32_t *dist, bool pregen, cudaStream_t st)
 {
     const EnvDims &d = env->d;
-    const int apw = d.L <= 48 ? 2 : 1;       // two agents per warp while the map fits 16 lanes x 3 rows
+    // two agents per warp (16 lanes x RPL rows each) while an agent's rows fit 18 words per lane: every map of up to 88 cells a side
+    const int apw = RW <= 3 ? 2 : 1;
     const int rpl = (d.L + 32 / apw - 1) / (32 / apw);
     const long warps = ((long)n * d.N + apw - 1) / apw;
-    const int grid = (int)((warps + kBfsWarps - 1) / kBfsWarps);
-#define MAPF_BFS_LAUNCH(RPL, APW) \
-    bfs_navi_kernel<RW, RPL, APW><<<grid, kBfsWarps * 32, 0, st>>>(d, ids, mask, n, env->obst, env->goal, env->navi, dist)
+    const int grid = pregen ? env->num_sms * 8 : (int)((warps + kBfsWarps - 1) / kBfsWarps);
+#define MAPF_BFS_LAUNCH(RPL, APW)                                                                                                   \
+    do {                                                                                                                            \
+        if (pregen)                                                                                                                 \
+            pregen_bfs_kernel<RW, RPL, APW><<<grid, kBfsWarps * 32, 0, st>>>(d, env->ro_prio, env->ro_work + 3, env->pg_obst,       \
+                                                                             env->pg_goal, env->navi, env->navi_alt, env->navi_sel); \
+        else                                                                                                                        \
+            bfs_navi_kernel<RW, RPL, APW><<<grid, kBfsWarps * 32, 0, st>>>(d, ids, mask, n, env->obst, env->goal, env->navi,         \
+                                                                           env->navi_alt, env->navi_sel, dist);                      \
+    } while (0)
     bool ok = true;
-    if (apw == 2) {
-        if constexpr (RW <= 2) {
-            switch (rpl) {
-                case 1: MAPF_BFS_LAUNCH(1, 2); break;
-                case 2: MAPF_BFS_LAUNCH(2, 2); break;
-                case 3: MAPF_BFS_LAUNCH(3, 2); break;
-                default: ok = false;
-            }
-        } else ok = false;
+    if constexpr (RW == 1) {
+        switch (rpl) {
+            case 1: MAPF_BFS_LAUNCH(1, 2); break;
+            case 2: MAPF_BFS_LAUNCH(2, 2); break;
+            default: ok = false;
+        }
+    } else if constexpr (RW == 2) {
+        switch (rpl) {
+            case 2: MAPF_BFS_LAUNCH(2, 2); break;
+            case 3: MAPF_BFS_LAUNCH(3, 2); break;
+            case 4: MAPF_BFS_LAUNCH(4, 2); break;
+            default: ok = false;
+        }
+    } else if constexpr (RW == 3) {
+        switch (rpl) {
+            case 4: MAPF_BFS_LAUNCH(4, 2); break;
+            case 5: MAPF_BFS_LAUNCH(5, 2); break;
+            case 6: MAPF_BFS_LAUNCH(6, 2); break;
+            default: ok = false;
+        }
     } else {
-        if constexpr (RW >= 2) {
-            switch (rpl) {
-                case 2: MAPF_BFS_LAUNCH(2, 1); break;
-                case 3: MAPF_BFS_LAUNCH(3, 1); break;
-                case 4: MAPF_BFS_LAUNCH(4, 1); break;
-                default: ok = false;
-            }
-        } else ok = false;
+        switch (rpl) {
+            case 3: MAPF_BFS_LAUNCH(3, 1); break;
+            case 4: MAPF_BFS_LAUNCH(4, 1); break;
+            default: ok = false;
+        }
     }
 #undef MAPF_BFS_LAUNCH
     if (!ok) {
@@ -269,14 +317,14 @@ static int launch_bfs_rw(mapf_env *env, const int32_t *ids, const uint8_t *mask,
     return MAPF_OK;
 }
 
-static int launch_bfs(mapf_env *env, const int32_t *d_env_ids, const uint8_t *d_mask, int n, int32_t *d_dist_out,
+static int launch_bfs(mapf_env *env, const int32_t *d_env_ids, const uint8_t *d_mask, int n, int32_t *d_dist_out, bool pregen,
                       cudaStream_t st)
 {
     switch (env->d.RW) {
-        case 1: return launch_bfs_rw<1>(env, d_env_ids, d_mask, n, d_dist_out, st);
-        case 2: return launch_bfs_rw<2>(env, d_env_ids, d_mask, n, d_dist_out, st);
-        case 3: return launch_bfs_rw<3>(env, d_env_ids, d_mask, n, d_dist_out, st);
-        case 4: return launch_bfs_rw<4>(env, d_env_ids, d_mask, n, d_dist_out, st);
+        case 1: return launch_bfs_rw<1>(env, d_env_ids, d_mask, n, d_dist_out, pregen, st);
+        case 2: return launch_bfs_rw<2>(env, d_env_ids, d_mask, n, d_dist_out, pregen, st);
+        case 3: return launch_bfs_rw<3>(env, d_env_ids, d_mask, n, d_dist_out, pregen, st);
+        case 4: return launch_bfs_rw<4>(env, d_env_ids, d_mask, n, d_dist_out, pregen, st);
     }
     mapf_set_error("unsupported map size");
     return MAPF_EINVAL;
@@ -284,14 +332,17 @@ static int launch_bfs(mapf_env *env, const int32_t *d_env_ids, const uint8_t *d_
 
 int mapf_launch_bfs(mapf_env *env, const int32_t *d_env_ids, int n, int32_t *d_dist_out, cudaStream_t st)
 {
-    return launch_bfs(env, d_env_ids, nullptr, n, d_dist_out, st);
+    return launch_bfs(env, d_env_ids, nullptr, n, d_dist_out, false, st);
 }
 
 // all B slots, skipping those whose mask byte is zero (NULL mask = all)
 int mapf_launch_bfs_masked(mapf_env *env, const uint8_t *d_mask, cudaStream_t st)
 {
-    return launch_bfs(env, nullptr, d_mask, env->d.B, nullptr, st);
+    return launch_bfs(env, nullptr, d_mask, env->d.B, nullptr, false, st);
 }
+
+// heuristic maps of the staged next instances listed in env->ro_prio (mapf_launch_pregen, mapf_reset_kernels.cu)
+int mapf_launch_pregen_bfs(mapf_env *env, cudaStream_t st) { return launch_bfs(env, nullptr, nullptr, 0, nullptr, true, st); }
 
 int mapf_launch_comm_mask(mapf_env *env, int k_nearest, uint8_t *d_out, cudaStream_t st)
 {
@@ -311,7 +362,7 @@ int mapf_launch_unpack(mapf_env *env, uint8_t *d_map, uint8_t *d_navi, cudaStrea
     }
     if (d_navi) {
         size_t total = (size_t)d.B * d.N * 4 * d.L * d.L;
-        unpack_navi_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(d, env->navi, d_navi);
+        unpack_navi_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(d, env->navi, env->navi_alt, env->navi_sel, d_navi);
         MAPF_CUDA(cudaGetLastError());
     }
     return MAPF_OK;

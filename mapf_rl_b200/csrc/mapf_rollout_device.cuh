@@ -56,6 +56,11 @@ struct RolloutArgs {
     // environments that will hit the step cap inside this launch (rollout_prio_kernel): taken first, all T steps in one item
     const uint32_t *prio;    // [0] count, [1 ..] environment ids
     const uint8_t *prio_flag;  // [B]
+    // pre-generated next instances (mapf_launch_pregen; NULL: every episode end re-generates in place)
+    uint8_t *pg_flag;        // [B] 1: staged
+    const uint32_t *pg_obst;
+    const uint8_t *pg_pos, *pg_goal;
+    uint8_t *navi_sel;       // [B]
 };
 
 // Which environments re-generate inside a launch of T steps is known up front for the step cap (steps + T > cap): those
@@ -63,14 +68,18 @@ struct RolloutArgs {
 // over all T steps; the rest of the batch follows as time-major chunks and fills in around them.  Without this the last
 // re-generations start late and the launch ends with a tail of a few warps.  One CTA (the scan is B loads).
 __global__ void rollout_prio_kernel(const int32_t *__restrict__ steps, int e0, int e1, int T, int cap, uint32_t *__restrict__ prio,
-                                    uint8_t *__restrict__ prio_flag)
+                                    uint8_t *__restrict__ prio_flag, uint8_t *__restrict__ pg_flag, unsigned long long *__restrict__ work)
 {
     __shared__ unsigned count;
-    if (threadIdx.x == 0) count = 0;
+    if (threadIdx.x == 0) {
+        count = 0;
+        work[2] = work[3] = 0ull;  // work counters of the pre-generation kernels that follow
+    }
     __syncthreads();
     for (int e = e0 + threadIdx.x; e < e1; e += blockDim.x) {
         const bool will = steps[e] + T > cap;
         prio_flag[e] = will ? 1 : 0;
+        pg_flag[e] = 0;  // set by pregen_reset_kernel once the slot's next instance is staged
         if (will) prio[1 + atomicAdd(&count, 1u)] = (uint32_t)e;
     }
     __syncthreads();
@@ -116,9 +125,13 @@ __device__ __forceinline__ void load_env_state(const StepParams &p, const int e,
             all_goal = all_goal && pp.x == gg.x && pp.y == gg.y;
         }
     }
-    int st = 0;
-    if (lane == 0) st = __ldcg(p.steps + e);
+    int st = 0, sel = 0;
+    if (lane == 0) {
+        st = __ldcg(p.steps + e);
+        sel = p.navi_alt ? __ldcg(p.navi_sel + e) : 0;
+    }
     r.step = __shfl_sync(MAPF_FULL_MASK, st, 0);
+    r.sel = __shfl_sync(MAPF_FULL_MASK, sel, 0);
     r.finished = __all_sync(MAPF_FULL_MASK, all_goal);
     asm volatile("cp.async.wait_all;" ::: "memory");
     __syncwarp();
@@ -141,28 +154,71 @@ __device__ __noinline__ void regenerate_env(const StepParams &p, const RolloutAr
     const unsigned long long g = r.env_offset + (unsigned long long)n * r.stride + (unsigned long long)e;
     uint32_t *obst = const_cast<uint32_t *>(p.obst);
     uint8_t *goal = const_cast<uint8_t *>(p.goal);
-    uint32_t *navi = const_cast<uint32_t *>(p.navi);
+    int sel = 0;
+    if (lane == 0 && p.navi_alt) sel = __ldcg(p.navi_sel + e);
+    sel = __shfl_sync(MAPF_FULL_MASK, sel, 0);
+    uint32_t *navi = const_cast<uint32_t *>(sel ? p.navi_alt : p.navi);  // the slot's live buffer
     reset_env_warp<RW, RW>(d, e, r.seed, g, r.density, obst, p.pos, goal, p.steps, p.err);
     __threadfence();
     __syncwarp();
     // get_navi_map (environment.py:195): the same warp-level BFS the load / reset path launches
-    // two agents at a time (one per half warp) while the map fits 16 lanes x 3 rows, else one.  (Two interleaved searches per
+    // two agents at a time (one per half warp) for maps of up to 88 cells a side, else one.  (Two interleaved searches per
     // half warp were measured too: a lone re-generation drops from 272 to 244 us, but the search then runs until the slowest
     // of FOUR agents is done and votes every third wave -- ~20 % more instructions -- and the rollout with episode handling got
     // slower, 27.9 -> 30.4 us per step at 2000 steps; profiles/r2_reset_cost.jsonl.)
-    bool two_per_warp = false;
-    if constexpr (RW <= 2) two_per_warp = d.L <= 48;  // 16 lanes x 3 rows (x 2 rows at RW = 1) hold the map
-    if (two_per_warp) {
-        if constexpr (RW <= 2) {
-            constexpr int RPL = RW == 1 ? 2 : 3;
+    if constexpr (RW <= 3) {
+        // 16 lanes x RPL rows hold the map: RPL = ceil(L / 16)
+        auto pairs = [&](auto rplc) {
+            constexpr int RPL = decltype(rplc)::value;
             for (int base = 0; base < d.N; base += 2) {
                 const int a = base + (lane >> 4);
                 bfs_navi_warp<RW, RPL, 2>(d, e, a < d.N ? a : 0, 0, a < d.N, obst, goal, navi, nullptr);
             }
+        };
+        const int rpl = (d.L + 15) >> 4;
+        if constexpr (RW == 1) {
+            if (rpl <= 1) pairs(std::integral_constant<int, 1>{});
+            else pairs(std::integral_constant<int, 2>{});
+        } else if constexpr (RW == 2) {
+            if (rpl <= 2) pairs(std::integral_constant<int, 2>{});
+            else if (rpl == 3) pairs(std::integral_constant<int, 3>{});
+            else pairs(std::integral_constant<int, 4>{});
+        } else {
+            if (rpl <= 4) pairs(std::integral_constant<int, 4>{});
+            else if (rpl == 5) pairs(std::integral_constant<int, 5>{});
+            else pairs(std::integral_constant<int, 6>{});
         }
     } else {
-        constexpr int RPL = RW < 2 ? 2 : RW;  // 32 lanes x RPL rows >= L for every L the RW class admits
+        constexpr int RPL = 4;  // 32 lanes x 4 rows >= L for every L the RW class admits
         for (int a = 0; a < d.N; ++a) bfs_navi_warp<RW, RPL, 1>(d, e, a, 0, true, obst, goal, navi, nullptr);
+    }
+    __threadfence();
+    __syncwarp();
+}
+
+// The episode of slot e has ended and its next instance was staged before the launch (mapf_launch_pregen): the staged obstacle
+// bitmap, starts and goals become the live ones and navi_sel[e] flips to the buffer that holds the instance's heuristic maps.
+__device__ __forceinline__ void adopt_pregenerated(const StepParams &p, const RolloutArgs &r, const int e)
+{
+    const EnvDims &d = p.d;
+    const int lane = threadIdx.x & 31;
+    {
+        const uint4 *src = reinterpret_cast<const uint4 *>(r.pg_obst + (size_t)e * d.obst_stride);
+        uint4 *dst = reinterpret_cast<uint4 *>(const_cast<uint32_t *>(p.obst) + (size_t)e * d.obst_stride);
+        for (int w = lane; w < (d.obst_stride >> 2); w += 32) dst[w] = __ldcg(src + w);
+    }
+    {
+        const uint16_t *sp = reinterpret_cast<const uint16_t *>(r.pg_pos) + (size_t)e * d.N;
+        const uint16_t *sg = reinterpret_cast<const uint16_t *>(r.pg_goal) + (size_t)e * d.N;
+        uint16_t *dp = reinterpret_cast<uint16_t *>(p.pos) + (size_t)e * d.N;
+        uint16_t *dg = reinterpret_cast<uint16_t *>(const_cast<uint8_t *>(p.goal)) + (size_t)e * d.N;
+        for (int a = lane; a < d.N; a += 32) dp[a] = __ldcg(sp + a), dg[a] = __ldcg(sg + a);
+    }
+    if (lane == 0) {
+        p.steps[e] = 0;
+        r.episode[e] = __ldcg(r.episode + e) + 1;
+        r.navi_sel[e] = __ldcg(r.navi_sel + e) ^ 1;
+        r.pg_flag[e] = 0;
     }
     __threadfence();
     __syncwarp();
@@ -267,7 +323,11 @@ rollout_kernel(const __grid_constant__ StepParams p0, const __grid_constant__ Ro
                 // slot and emits the new episode's first observation
                 const int st = __shfl_sync(MAPF_FULL_MASK, regs.step, 0);
                 if (regs.finished || st >= r.max_steps) {
-                    regenerate_env<RW>(p0, r, e);
+                    int staged = 0;
+                    if (r.pg_flag && lane == 0) staged = __ldcg(r.pg_flag + e);
+                    staged = __shfl_sync(MAPF_FULL_MASK, staged, 0);
+                    if (staged) adopt_pregenerated(p0, r, e);
+                    else regenerate_env<RW>(p0, r, e);
                     {
                         int keep[K];   // load_env_state starts a fresh EnvRegs; the prefetched actions stay
 #pragma unroll

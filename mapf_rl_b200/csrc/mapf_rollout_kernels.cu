@@ -39,6 +39,18 @@ void mapf_set_rollout_tuning(int warps_per_sm, int chunk, int store_mode, int st
 
 bool mapf_rollout_supported(const mapf_env *env) { return env->d.K <= 2; }
 
+// MAPF_ROLLOUT_PREGEN=0 / mapf_debug_rollout_pregen(0): episodes that end inside a rollout launch always re-generate in place
+int &rollout_pregen_ref()
+{
+    static int v = [] {
+        const char *s = std::getenv("MAPF_ROLLOUT_PREGEN");
+        return s ? std::atoi(s) : 1;
+    }();
+    return v;
+}
+void mapf_set_rollout_pregen(int on) { rollout_pregen_ref() = on; }
+int mapf_launch_pregen(mapf_env *env, cudaStream_t st);
+
 // The persistent rollout over environments [e0, e1); MAPF_EINVAL = geometry not served (the caller uses chains of launches).
 int mapf_launch_rollout(mapf_env *env, int e0, int e1, int T, const uint8_t *d_actions, int action_slots, uint8_t *d_obs, int obs_slots,
                         const StepOut &out, int out_slots, cudaStream_t st)
@@ -57,12 +69,27 @@ int mapf_launch_rollout(mapf_env *env, int e0, int e1, int T, const uint8_t *d_a
     r.seed = env->ar_seed, r.env_offset = env->ar_offset, r.stride = env->ar_stride, r.density = env->ar_density;
     r.episode = env->ro_episode;
     static const int use_prio = [] { const char *v = std::getenv("MAPF_ROLLOUT_PRIO"); return v ? std::atoi(v) : 1; }();
-    r.prio = nullptr, r.prio_flag = nullptr;
-    if (use_prio && r.max_steps > 0 && T <= r.max_steps / 2) {
-        // few environments hit the cap inside this launch: list them so that they are taken first (rollout_prio_kernel)
-        rollout_prio_kernel<<<1, 1024, 0, st>>>(env->steps, e0, e1, T, r.max_steps, env->ro_prio, env->ro_prio_flag);
-        MAPF_CUDA(cudaGetLastError());
-        r.prio = env->ro_prio, r.prio_flag = env->ro_prio_flag;
+    r.prio = nullptr, r.prio_flag = nullptr, r.pg_flag = nullptr;
+    if (r.max_steps > 0) {
+        // the environments that hit the cap inside this launch are known up front (rollout_prio_kernel) ...
+        const bool pregen = rollout_pregen_ref() != 0 && env->navi_alt != nullptr;
+        const bool prio = use_prio && !pregen && T <= r.max_steps / 2;
+        if (pregen || prio) {
+            rollout_prio_kernel<<<1, 1024, 0, st>>>(env->steps, e0, e1, T, r.max_steps, env->ro_prio, env->ro_prio_flag, env->pg_flag,
+                                                    env->ro_work);
+            MAPF_CUDA(cudaGetLastError());
+        }
+        if (pregen) {
+            // ... their next instances are generated now, by the dedicated generator / BFS kernels at full occupancy, into the
+            // staging arrays and the second heuristic-map buffer; the rollout kernel adopts them at the episode's end
+            const int rc = mapf_launch_pregen(env, st);
+            if (rc != MAPF_OK) return rc;
+            r.pg_flag = env->pg_flag, r.pg_obst = env->pg_obst, r.pg_pos = env->pg_pos, r.pg_goal = env->pg_goal;
+            r.navi_sel = env->navi_sel;
+        } else if (prio) {
+            // ... or, without the staging memory, they are the long items of the launch and are handed out first
+            r.prio = env->ro_prio, r.prio_flag = env->ro_prio_flag;
+        }
     }
     // occupancy class: the smallest one that holds the requested warps
     const RolloutTuning &tn = rollout_tuning();

@@ -118,6 +118,7 @@ struct EnvRegs {
     int act_next[K];   // the action of the NEXT step, requested one step ahead (the only global load of a resident step)
     int step;          // step counter
     bool finished;     // all agents stood on their goals after the last step (environment.py:415)
+    int sel;           // navi_sel[e]: which heuristic-map buffer holds the live instance
 };
 
 // One warp, one environment: Environment.step (DO_STEP) and the observation BIT stream of all its agents.
@@ -145,6 +146,12 @@ __device__ __forceinline__ void env_step_gather(const StepParams &p, const int e
     // the same time).  It is never cleared: an entry is trusted only if it round-trips through s_cell.
     uint8_t *s_occ = reinterpret_cast<uint8_t *>(s_bits);
     const bool navi_keep = p.flags & MAPF_STEPF_NAVI_KEEP;
+    // the buffer that holds the slot's live heuristic maps (mapf_common.cuh)
+    [[maybe_unused]] const uint32_t *navi_live = p.navi;
+    if constexpr (DO_OBS) {
+        if constexpr (RESIDENT) navi_live = out.sel ? p.navi_alt : p.navi;
+        else if (p.navi_alt && __ldg(p.navi_sel + e)) navi_live = p.navi_alt;
+    }
     {
         // ---- request every input of this env up front ----
         if constexpr (!RESIDENT) {
@@ -369,7 +376,7 @@ __device__ __forceinline__ void env_step_gather(const StepParams &p, const int e
                 const int a = k * 32 + lane;
                 const int tid = (px[k] >> 3) * d.NB + (py[k] >> 3);
                 if (valid[k] && tid != tile[k]) {
-                    const uint4 *src = reinterpret_cast<const uint4 *>(p.navi + ((size_t)e * N + a) * d.navi_agent_stride) + ((size_t)tid << 3);
+                    const uint4 *src = reinterpret_cast<const uint4 *>(navi_live + ((size_t)e * N + a) * d.navi_agent_stride) + ((size_t)tid << 3);
                     const uint32_t dst = smem_addr(s_tiles + (size_t)a * kTileStride);
 #pragma unroll
                     for (int j = 0; j < 8; ++j)
@@ -398,7 +405,7 @@ __device__ __forceinline__ void env_step_gather(const StepParams &p, const int e
                 // navi tile (x >> 3, y >> 3), rows (x & 7) .. (x & 7) + 8 of one 128-byte line
                 uint2 wr[9];
                 if constexpr (!RESIDENT) {
-                    const uint2 *nb = reinterpret_cast<const uint2 *>(p.navi + ((size_t)e * N + a) * d.navi_agent_stride) +
+                    const uint2 *nb = reinterpret_cast<const uint2 *>(navi_live + ((size_t)e * N + a) * d.navi_agent_stride) +
                                       ((size_t)((x >> 3) * d.NB + (y >> 3)) << 4) + (x & 7);
 #ifdef MAPF_ENABLE_DIAG
                     if (p.flags & MAPF_STEPF_DIAG_NO_NAVI) {

@@ -201,6 +201,8 @@ StepParams mapf_make_step_params(const mapf_env *env)
     p.pos = env->pos;
     p.goal = env->goal;
     p.navi = env->navi;
+    p.navi_alt = env->navi_alt;
+    p.navi_sel = env->navi_sel;
     p.steps = env->steps;
     p.err = env->err;
     for (int i = 0; i < 5; ++i) p.r[i] = env->reward[i];

@@ -147,6 +147,7 @@ def test_full_pkl_rollout_vs_oracle(N, stream):
     (3, 5, 0.0, None), (4, 9, 0.1, None), (6, 30, 0.0, None), (8, 33, 0.05, None), (12, 64, 0.1, None),
     (10, 7, 0.3, None), (20, 6, 0.3, None), (33, 37, 0.25, None), (56, 40, 0.3, None), (57, 12, 0.3, None),
     (80, 64, 0.3, None), (88, 100, 0.2, None), (89, 8, 0.3, None), (120, 128, 0.1, None), (7, 45, 0.0, None),
+    (28, 10, 0.2, None), (72, 33, 0.3, None),
 ])
 def test_random_grids_vs_oracle(L, N, density, occupancy):
     """Generic sizes: every RW (row words) / K (agents per lane) template, unaligned observation blocks,

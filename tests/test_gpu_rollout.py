@@ -389,15 +389,20 @@ def test_rollout_full_size_c3_c4_vs_oracle(rollout_tuning, B, N, L, name):
 
 @pytest.mark.parametrize("B,N,L,cap,chunk,store", [(300, 1, 6, 9, 0, 0), (257, 2, 7, 6, 3, 1), (600, 8, 12, 5, 4, 0),
                                                      (96, 32, 40, 4, 2, 1), (40, 64, 40, 3, 5, 0), (24, 40, 64, 4, 0, 0)])
-def test_rollout_autoreset_vs_twin(rollout_tuning, B, N, L, cap, chunk, store):
+@pytest.mark.parametrize("pregen", [1, 0])
+def test_rollout_autoreset_vs_twin(rollout_tuning, B, N, L, cap, chunk, store, pregen):
     """Episode handling inside the launch (worker.py:390,422-428): a step that finds its environment finished -- all agents
     on their goals after the previous step (tiny boards reach that within a few random steps), or `cap` steps taken --
     re-generates the slot and emits the first observation.  The twin does the same through the public pieces:
-    reset(mask, env_offset = base + n * stride) + observe, else step."""
+    reset(mask, env_offset = base + n * stride) + observe, else step.
+    pregen = 1: the first episode end of a slot in a launch adopts an instance staged by the dedicated generator / BFS
+    kernels before the launch (double-buffered heuristic maps), later ones re-generate inside the kernel; 0: always inside."""
     import torch
+    from mapf_rl_b200 import _native
     T, A = 23, 5
     seed, base, stride, density = 77, 1000, 4096, 0.2
     rollout_tuning(1, 0, chunk, store)
+    _native.lib().mapf_debug_rollout_pregen(pregen)
     env, twin = make_env(B, N, L), make_env(B, N, L)
     for e in (env, twin):
         e.reset(seed=seed, env_offset=base, density=density)
@@ -406,7 +411,15 @@ def test_rollout_autoreset_vs_twin(rollout_tuning, B, N, L, cap, chunk, store):
     g.manual_seed(11)
     acts = torch.randint(0, 5, (A, B, N), generator=g, device="cuda", dtype=torch.uint8)
     codes = torch.zeros((T, B, N), dtype=torch.uint8, device="cuda")
-    obs, rew, done, steps = env.rollout(acts, num_steps=T, out_codes=codes)
+    if chunk % 2 == 0:
+        obs, rew, done, steps = env.rollout(acts, num_steps=T, out_codes=codes)
+    else:
+        # two calls: the second one starts from flipped heuristic-map buffers and staged flags of the first
+        T1 = 11
+        parts = [env.rollout(acts, num_steps=T1, out_codes=codes[:T1]),
+                 env.rollout(torch.roll(acts, shifts=-(T1 % A), dims=0), num_steps=T - T1, out_codes=codes[T1:])]
+        obs, rew, done, steps = (torch.cat([a.clone(), b]) for a, b in zip(*parts))
+    _native.lib().mapf_debug_rollout_pregen(1)
     episode = np.zeros(B, dtype=np.int64)
     fin = np.zeros(B, dtype=bool)
     n_resets = n_done = 0
@@ -448,6 +461,9 @@ def test_rollout_autoreset_vs_twin(rollout_tuning, B, N, L, cap, chunk, store):
     twin.step(acts[0])
     o2, _, _ = twin.step(acts[1])
     assert torch.equal(o1[1], o2)
+    # ... and through the single-step kernels (they read the live heuristic-map buffer too)
+    assert torch.equal(env.step(acts[2])[0], twin.step(acts[2])[0])
+    assert torch.equal(env.observe()[0], twin.observe()[0])
 
 
 def test_rollout_bad_arguments():
