@@ -198,9 +198,13 @@ int mapf_env_create(const mapf_env_config *cfg, mapf_env **out)
     if (rc == MAPF_OK) rc = dev_alloc(&env->ro_episode, (size_t)d.B, &total);
     if (rc == MAPF_OK) rc = dev_alloc(&env->ro_prio, (size_t)d.B + 1, &total);
     if (rc == MAPF_OK) rc = dev_alloc(&env->ro_prio_flag, (size_t)d.B, &total);
+    env->ro_tq_cap = d.B + 32;  // >= one re-generation in flight per slot
+    if (rc == MAPF_OK) rc = dev_alloc(&env->ro_tq, (size_t)env->ro_tq_cap * 4 + 4, &total);
     if (rc == MAPF_OK) {
         cudaError_t e2 = cudaMemset(env->obst, 0, (size_t)d.B * d.obst_stride * 4);
         if (e2 == cudaSuccess) e2 = cudaMemset(env->ro_work, 0, 32);
+        if (e2 == cudaSuccess) e2 = cudaMemset(env->ro_tq, 0x80, ((size_t)env->ro_tq_cap * 4 + 4) * 4);  // every entry free
+        if (e2 == cudaSuccess) e2 = cudaMemset(env->ro_tq, 0, 16);
         if (e2 == cudaSuccess) e2 = cudaMemset(env->navi_sel, 0, (size_t)d.B);
         if (e2 == cudaSuccess) e2 = cudaMemset(env->pg_flag, 0, (size_t)d.B);
         if (e2 == cudaSuccess) e2 = cudaMemset(env->ro_progress, 0, (size_t)d.B * 4);
@@ -254,6 +258,7 @@ int mapf_env_destroy(mapf_env *env)
     if (env->hp_stepped) cudaEventDestroy(env->hp_stepped);
     cudaFree(env->ro_prio);
     cudaFree(env->ro_prio_flag);
+    cudaFree(env->ro_tq);
     cudaFree(env->d_actions);
     cudaFree(env->d_obs);
     cudaFree(env->d_rewards);

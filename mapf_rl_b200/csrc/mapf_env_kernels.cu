@@ -127,13 +127,14 @@ bfs_navi_kernel(EnvDims d, const int32_t *__restrict__ env_ids, const uint8_t *_
 // known on the device, so a fixed grid claims (slot, agent group) items from a counter.
 template <int RW, int RPL, int APW>
 __global__ void __launch_bounds__(kBfsWarps * 32, RW * RPL <= 9 ? 8 : 1)
-pregen_bfs_kernel(EnvDims d, const uint32_t *__restrict__ list, unsigned long long *__restrict__ counter,
+pregen_bfs_kernel(EnvDims d, const uint32_t *__restrict__ list, int min_count, unsigned long long *__restrict__ counter,
                   const uint32_t *__restrict__ pg_obst, const uint8_t *__restrict__ pg_goal, uint32_t *__restrict__ navi,
                   uint32_t *__restrict__ navi_alt, const uint8_t *__restrict__ navi_sel)
 {
     constexpr int LW = 32 / APW;
     const int lane = lane_id();
     const unsigned groups = (unsigned)(d.N + APW - 1) / APW;
+    if (list[0] < (unsigned)min_count) return;
     const unsigned long long items = (unsigned long long)list[0] * groups;
     for (;;) {
         unsigned long long it = 0;
@@ -261,10 +262,11 @@ int mapf_launch_validate_state(mapf_env *env, const int32_t *d_env_ids, int n, c
     return MAPF_OK;
 }
 
-// pregen = true: pregen_bfs_kernel over the list in env->ro_prio (ids / mask / n / dist unused)
+// pregen_min >= 0: pregen_bfs_kernel over the list in env->ro_prio (ids / mask / n / dist unused)
 template <int RW>
-static int launch_bfs_rw(mapf_env *env, const int32_t *ids, const uint8_t *mask, int n, int32_t *dist, bool pregen, cudaStream_t st)
+static int launch_bfs_rw(mapf_env *env, const int32_t *ids, const uint8_t *mask, int n, int32_t *dist, int pregen_min, cudaStream_t st)
 {
+    const bool pregen = pregen_min >= 0;
     const EnvDims &d = env->d;
     // two agents per warp (16 lanes x RPL rows each) while an agent's rows fit 18 words per lane: every map of up to 88 cells a side
     const int apw = RW <= 3 ? 2 : 1;
@@ -274,7 +276,7 @@ static int launch_bfs_rw(mapf_env *env, const int32_t *ids, const uint8_t *mask,
 #define MAPF_BFS_LAUNCH(RPL, APW)                                                                                                   \
     do {                                                                                                                            \
         if (pregen)                                                                                                                 \
-            pregen_bfs_kernel<RW, RPL, APW><<<grid, kBfsWarps * 32, 0, st>>>(d, env->ro_prio, env->ro_work + 3, env->pg_obst,       \
+            pregen_bfs_kernel<RW, RPL, APW><<<grid, kBfsWarps * 32, 0, st>>>(d, env->ro_prio, pregen_min, env->ro_work + 3, env->pg_obst, \
                                                                              env->pg_goal, env->navi, env->navi_alt, env->navi_sel); \
         else                                                                                                                        \
             bfs_navi_kernel<RW, RPL, APW><<<grid, kBfsWarps * 32, 0, st>>>(d, ids, mask, n, env->obst, env->goal, env->navi,         \
@@ -317,14 +319,14 @@ static int launch_bfs_rw(mapf_env *env, const int32_t *ids, const uint8_t *mask,
     return MAPF_OK;
 }
 
-static int launch_bfs(mapf_env *env, const int32_t *d_env_ids, const uint8_t *d_mask, int n, int32_t *d_dist_out, bool pregen,
+static int launch_bfs(mapf_env *env, const int32_t *d_env_ids, const uint8_t *d_mask, int n, int32_t *d_dist_out, int pregen_min,
                       cudaStream_t st)
 {
     switch (env->d.RW) {
-        case 1: return launch_bfs_rw<1>(env, d_env_ids, d_mask, n, d_dist_out, pregen, st);
-        case 2: return launch_bfs_rw<2>(env, d_env_ids, d_mask, n, d_dist_out, pregen, st);
-        case 3: return launch_bfs_rw<3>(env, d_env_ids, d_mask, n, d_dist_out, pregen, st);
-        case 4: return launch_bfs_rw<4>(env, d_env_ids, d_mask, n, d_dist_out, pregen, st);
+        case 1: return launch_bfs_rw<1>(env, d_env_ids, d_mask, n, d_dist_out, pregen_min, st);
+        case 2: return launch_bfs_rw<2>(env, d_env_ids, d_mask, n, d_dist_out, pregen_min, st);
+        case 3: return launch_bfs_rw<3>(env, d_env_ids, d_mask, n, d_dist_out, pregen_min, st);
+        case 4: return launch_bfs_rw<4>(env, d_env_ids, d_mask, n, d_dist_out, pregen_min, st);
     }
     mapf_set_error("unsupported map size");
     return MAPF_EINVAL;
@@ -332,17 +334,20 @@ static int launch_bfs(mapf_env *env, const int32_t *d_env_ids, const uint8_t *d_
 
 int mapf_launch_bfs(mapf_env *env, const int32_t *d_env_ids, int n, int32_t *d_dist_out, cudaStream_t st)
 {
-    return launch_bfs(env, d_env_ids, nullptr, n, d_dist_out, false, st);
+    return launch_bfs(env, d_env_ids, nullptr, n, d_dist_out, -1, st);
 }
 
 // all B slots, skipping those whose mask byte is zero (NULL mask = all)
 int mapf_launch_bfs_masked(mapf_env *env, const uint8_t *d_mask, cudaStream_t st)
 {
-    return launch_bfs(env, nullptr, d_mask, env->d.B, nullptr, false, st);
+    return launch_bfs(env, nullptr, d_mask, env->d.B, nullptr, -1, st);
 }
 
 // heuristic maps of the staged next instances listed in env->ro_prio (mapf_launch_pregen, mapf_reset_kernels.cu)
-int mapf_launch_pregen_bfs(mapf_env *env, cudaStream_t st) { return launch_bfs(env, nullptr, nullptr, 0, nullptr, true, st); }
+int mapf_launch_pregen_bfs(mapf_env *env, int min_count, cudaStream_t st)
+{
+    return launch_bfs(env, nullptr, nullptr, 0, nullptr, min_count < 0 ? 0 : min_count, st);
+}
 
 int mapf_launch_comm_mask(mapf_env *env, int k_nearest, uint8_t *d_out, cudaStream_t st)
 {

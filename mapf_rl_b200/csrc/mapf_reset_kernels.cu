@@ -23,13 +23,14 @@ reset_kernel(EnvDims d, const uint8_t *__restrict__ mask, uint64_t seed, uint64_
 // end.  The list's length is only known on the device: a fixed grid claims list entries from a counter.
 template <int RW, int RPL>
 __global__ void __launch_bounds__(128)
-pregen_reset_kernel(EnvDims d, const uint32_t *__restrict__ list, unsigned long long *__restrict__ counter, uint64_t seed,
+pregen_reset_kernel(EnvDims d, const uint32_t *__restrict__ list, int min_count, unsigned long long *__restrict__ counter, uint64_t seed,
                     uint64_t env_offset, uint64_t stride, float density, const uint32_t *__restrict__ episode,
                     uint32_t *__restrict__ pg_obst, uint8_t *__restrict__ pg_pos, uint8_t *__restrict__ pg_goal,
                     int32_t *__restrict__ pg_steps, uint8_t *__restrict__ pg_flag, int32_t *__restrict__ err)
 {
     const int lane = threadIdx.x & 31;
     const unsigned long long count = list[0];
+    if (count < (unsigned long long)min_count) return;  // few: the rollout kernel re-generates them itself
     for (;;) {
         unsigned long long it = 0;
         if (lane == 0) it = atomicAdd(counter, 1ull);
@@ -43,16 +44,17 @@ pregen_reset_kernel(EnvDims d, const uint32_t *__restrict__ list, unsigned long 
 }
 
 template <int RW>
-int launch_reset_rw(mapf_env *env, const uint8_t *mask, uint64_t seed, uint64_t off, float density, bool pregen, cudaStream_t st)
+int launch_reset_rw(mapf_env *env, const uint8_t *mask, uint64_t seed, uint64_t off, float density, int pregen_min, cudaStream_t st)
 {
     const EnvDims &d = env->d;
     const int rpl = (d.L + 31) / 32;
     const int warps = 4;
+    const bool pregen = pregen_min >= 0;
     const int grid = pregen ? env->num_sms * 4 : (d.B + warps - 1) / warps;
 #define MAPF_RESET_LAUNCH(RPL)                                                                                                   \
     do {                                                                                                                         \
         if (pregen)                                                                                                              \
-            pregen_reset_kernel<RW, RPL><<<grid, warps * 32, 0, st>>>(d, env->ro_prio, env->ro_work + 2, env->ar_seed,           \
+            pregen_reset_kernel<RW, RPL><<<grid, warps * 32, 0, st>>>(d, env->ro_prio, pregen_min, env->ro_work + 2, env->ar_seed, \
                                                                       env->ar_offset, env->ar_stride, env->ar_density,           \
                                                                       env->ro_episode, env->pg_obst, env->pg_pos, env->pg_goal,  \
                                                                       env->pg_steps, env->pg_flag, env->err);                    \
@@ -75,16 +77,16 @@ int launch_reset_rw(mapf_env *env, const uint8_t *mask, uint64_t seed, uint64_t 
 }  // namespace
 
 int mapf_launch_bfs_masked(mapf_env *env, const uint8_t *d_mask, cudaStream_t st);
-int mapf_launch_pregen_bfs(mapf_env *env, cudaStream_t st);
+int mapf_launch_pregen_bfs(mapf_env *env, int min_count, cudaStream_t st);
 
-static int launch_reset(mapf_env *env, const uint8_t *d_mask, uint64_t seed, uint64_t env_offset, float density, bool pregen,
+static int launch_reset(mapf_env *env, const uint8_t *d_mask, uint64_t seed, uint64_t env_offset, float density, int pregen_min,
                         cudaStream_t st)
 {
     switch (env->d.RW) {
-        case 1: return launch_reset_rw<1>(env, d_mask, seed, env_offset, density, pregen, st);
-        case 2: return launch_reset_rw<2>(env, d_mask, seed, env_offset, density, pregen, st);
-        case 3: return launch_reset_rw<3>(env, d_mask, seed, env_offset, density, pregen, st);
-        case 4: return launch_reset_rw<4>(env, d_mask, seed, env_offset, density, pregen, st);
+        case 1: return launch_reset_rw<1>(env, d_mask, seed, env_offset, density, pregen_min, st);
+        case 2: return launch_reset_rw<2>(env, d_mask, seed, env_offset, density, pregen_min, st);
+        case 3: return launch_reset_rw<3>(env, d_mask, seed, env_offset, density, pregen_min, st);
+        case 4: return launch_reset_rw<4>(env, d_mask, seed, env_offset, density, pregen_min, st);
     }
     mapf_set_error("unsupported map size");
     return MAPF_EINVAL;
@@ -93,16 +95,16 @@ static int launch_reset(mapf_env *env, const uint8_t *d_mask, uint64_t seed, uin
 int mapf_launch_reset(mapf_env *env, const uint8_t *d_mask, uint64_t seed, uint64_t env_offset, float density,
                       cudaStream_t st)
 {
-    const int rc = launch_reset(env, d_mask, seed, env_offset, density, false, st);
+    const int rc = launch_reset(env, d_mask, seed, env_offset, density, -1, st);
     if (rc != MAPF_OK) return rc;
     return mapf_launch_bfs_masked(env, d_mask, st);  // get_navi_map, environment.py:195
 }
 
 // Episode handling of mapf_env_rollout: the next instance of every slot listed in env->ro_prio (rollout_prio_kernel), generator
 // + heuristic maps at the full occupancy of the dedicated kernels, staged for the rollout kernel to adopt (mapf_common.cuh).
-int mapf_launch_pregen(mapf_env *env, cudaStream_t st)
+int mapf_launch_pregen(mapf_env *env, int min_count, cudaStream_t st)
 {
-    const int rc = launch_reset(env, nullptr, 0, 0, 0.f, true, st);
+    const int rc = launch_reset(env, nullptr, 0, 0, 0.f, min_count < 0 ? 0 : min_count, st);
     if (rc != MAPF_OK) return rc;
-    return mapf_launch_pregen_bfs(env, st);
+    return mapf_launch_pregen_bfs(env, min_count, st);
 }

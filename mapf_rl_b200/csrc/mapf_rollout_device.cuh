@@ -61,7 +61,24 @@ struct RolloutArgs {
     const uint32_t *pg_obst;
     const uint8_t *pg_pos, *pg_goal;
     uint8_t *navi_sel;       // [B]
+    int pregen_min;          // the pre-generation kernels ran iff the list holds at least this many environments
+    // BFS task queue of in-launch re-generations (NULL: the re-generating warp searches for every agent itself)
+    uint32_t *tq;            // [0] head (hint), [1] tail, [4 ..] ring of tq_cap entries {slot, next group, groups done, -}
+    int tq_cap;
+#ifdef MAPF_ENABLE_DIAG
+    unsigned long long *trace;  // [1 + 8 * capacity]: [0] records written; per item {item, env, claimed, loaded, regen_ns, regens, done, smid}
+    int trace_cap;
+#endif
 };
+
+#ifdef MAPF_ENABLE_DIAG
+__device__ __forceinline__ unsigned long long diag_now()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+#endif
 
 // Which environments re-generate inside a launch of T steps is known up front for the step cap (steps + T > cap): those
 // are the long items (a re-generation is ~80 steps of work), so they are listed here and handed out FIRST, each as one item
@@ -137,11 +154,128 @@ __device__ __forceinline__ void load_env_state(const StepParams &p, const int e,
     __syncwarp();
 }
 
-// worker.py:422-428 inside the launch: a new instance for slot e (generator + heuristic maps of all its agents), by this
-// warp alone.  Instance number n of slot e is global instance env_offset + n * stride + e of the Philox stream, i.e. what
-// mapf_env_reset(mask = {e}, seed, env_offset + n * stride) draws.  Kept out of line: it runs once per episode.
+// The heuristic maps of agent group `grp` of slot e (two agents, one per half warp, for maps of up to 88 cells a side, else
+// one) into the slot's live buffer: get_navi_map (environment.py:195) with the warp-level BFS of the load / reset path.
 template <int RW>
-__device__ __noinline__ void regenerate_env(const StepParams &p, const RolloutArgs &r, const int e)
+__device__ __forceinline__ int bfs_groups(const EnvDims &d) { return RW <= 3 ? (d.N + 1) >> 1 : d.N; }
+
+template <int RW>
+__device__ __noinline__ void bfs_group(const StepParams &p, const int e, const int grp)
+{
+    const EnvDims &d = p.d;
+    const int lane = threadIdx.x & 31;
+    const uint32_t *obst = p.obst;
+    const uint8_t *goal = p.goal;
+    int sel = 0;
+    if (lane == 0 && p.navi_alt) sel = __ldcg(p.navi_sel + e);
+    sel = __shfl_sync(MAPF_FULL_MASK, sel, 0);
+    uint32_t *navi = const_cast<uint32_t *>(sel ? p.navi_alt : p.navi);  // the slot's live buffer
+    if constexpr (RW <= 3) {
+        // 16 lanes x RPL rows hold the map: RPL = ceil(L / 16)
+        const int a = 2 * grp + (lane >> 4);
+        auto pair = [&](auto rplc) {
+            constexpr int RPL = decltype(rplc)::value;
+            bfs_navi_warp<RW, RPL, 2>(d, e, a < d.N ? a : 0, 0, a < d.N, obst, goal, navi, nullptr);
+        };
+        const int rpl = (d.L + 15) >> 4;
+        if constexpr (RW == 1) {
+            if (rpl <= 1) pair(std::integral_constant<int, 1>{});
+            else pair(std::integral_constant<int, 2>{});
+        } else if constexpr (RW == 2) {
+            if (rpl <= 2) pair(std::integral_constant<int, 2>{});
+            else if (rpl == 3) pair(std::integral_constant<int, 3>{});
+            else pair(std::integral_constant<int, 4>{});
+        } else {
+            if (rpl <= 4) pair(std::integral_constant<int, 4>{});
+            else if (rpl == 5) pair(std::integral_constant<int, 5>{});
+            else pair(std::integral_constant<int, 6>{});
+        }
+    } else {
+        bfs_navi_warp<RW, 4, 1>(d, e, grp, 0, true, obst, goal, navi, nullptr);  // 32 lanes x 4 rows >= L
+    }
+}
+
+// ---- BFS task queue -------------------------------------------------------------------------------------------------
+// A re-generation is the generator (one warp, serial over the agents) followed by one BFS per agent group -- independent
+// searches, ~2/3 of the work.  The re-generating warp announces them in a ring entry {slot, next group, groups done}; every
+// warp looks at the open entries before it claims its next work item and takes a group with ONE fetch-and-add on the
+// entry's `next` word (no retry loops: thousands of warps arrive at once), so the searches of one slot run on many warps and
+// a re-generation takes the generator's time plus about one search instead of all of them in sequence.
+// A free entry has next = kTqFree (negative as int32, far from wrapping): a claim succeeds iff 0 <= claimed < groups.  The
+// owner publishes slot BEFORE it zeroes next and frees the entry (next first) only after every group is done, so a
+// successful claim always reads the slot it belongs to, whatever incarnation of the entry a late warp runs into.
+constexpr uint32_t kTqFree = 0x80808080u;  // never used: the cudaMemset(0x80) pattern
+constexpr uint32_t kTqDone = 0xC0C0C0C0u;  // its re-generation is complete
+constexpr int kTqUnpublished = -2;         // tq_claim: reserved by an owner that has not published it yet (or never used)
+
+__device__ __forceinline__ uint32_t *tq_entry(const RolloutArgs &r, const uint32_t idx) { return r.tq + 4 + 4 * (idx % (uint32_t)r.tq_cap); }
+
+// claims one group of ring entry `ent`: >= 0 the group (and `e` the slot), -1 none left, kTqUnpublished
+template <int RW>
+__device__ __forceinline__ int tq_claim(const StepParams &p, uint32_t *ent, const int lane, int &e)
+{
+    int g = -1, slot = 0;
+    if (lane == 0) {
+        const int32_t c = (int32_t)atomicAdd(ent + 1, 1u);
+        if (c >= 0 && c < bfs_groups<RW>(p.d)) {
+            __threadfence();  // the claim before the slot (published before next was zeroed)
+            g = c;
+            slot = (int)ld_acquire_u32(ent);
+        } else if (c < (int32_t)0xA0000000u) {
+            g = kTqUnpublished;
+        }
+    }
+    g = __shfl_sync(MAPF_FULL_MASK, g, 0);
+    e = __shfl_sync(MAPF_FULL_MASK, slot, 0);
+    return g;
+}
+
+template <int RW>
+__device__ __forceinline__ void tq_run(const StepParams &p, uint32_t *ent, const int e, const int g, const int lane)
+{
+    bfs_group<RW>(p, e, g);
+    __syncwarp();
+    if (lane == 0) {
+        __threadfence();  // the tiles before the count
+        atomicAdd(ent + 2, 1u);
+    }
+}
+
+// A warp between two work items lends a hand: it looks at ONE announced entry, picked pseudo-randomly among those past the
+// head hint (thousands of warps come by while a few hundred re-generations are open: walking every entry would cost each of
+// them one L2 round trip per entry, and all of them would crowd the same one), takes up to two of its groups and goes back
+// to its own items.  An entry found exhausted right at the head moves the hint forward.
+template <int RW>
+__device__ __forceinline__ void tq_help(const StepParams &p, const RolloutArgs &r, const int lane, const uint32_t salt)
+{
+    uint32_t h = 0, t = 0;
+    if (lane == 0) h = __ldcg(r.tq), t = __ldcg(r.tq + 1);
+    h = __shfl_sync(MAPF_FULL_MASK, h, 0);
+    t = __shfl_sync(MAPF_FULL_MASK, t, 0);
+    const int32_t open = (int32_t)(t - h);
+    if (open <= 0) return;
+    const uint32_t idx = h + (uint32_t)(((unsigned long long)(salt * 2654435761u) * (uint32_t)open) >> 32);
+    uint32_t *ent = tq_entry(r, idx);
+    int e, g = -1;
+    for (int k = 0; k < 2; ++k) {
+        g = tq_claim<RW>(p, ent, lane, e);
+        if (g < 0) break;
+        tq_run<RW>(p, ent, e, g, lane);
+    }
+    if (g == -1 && idx == h && lane == 0) atomicMax(r.tq, h + 1);
+}
+
+// worker.py:422-428 inside the launch: a new instance for slot e (generator + heuristic maps of all its agents).  Instance
+// number n of slot e is global instance env_offset + n * stride + e of the Philox stream, i.e. what
+// mapf_env_reset(mask = {e}, seed, env_offset + n * stride) draws.  Kept out of line: it runs once per episode.
+// (Two interleaved searches per half warp were measured too: a lone re-generation drops from 272 to 244 us, but ~20 % more
+// instructions, and the rollout with episode handling got slower; profiles/r2_reset_cost.jsonl.)
+template <int RW>
+__device__ __noinline__ void regenerate_env(const StepParams &p, const RolloutArgs &r, const int e
+#ifdef MAPF_ENABLE_DIAG
+                                            , unsigned long long &gen_ns
+#endif
+)
 {
     const EnvDims &d = p.d;
     const int lane = threadIdx.x & 31;
@@ -152,45 +286,48 @@ __device__ __noinline__ void regenerate_env(const StepParams &p, const RolloutAr
     }
     n = __shfl_sync(MAPF_FULL_MASK, n, 0);
     const unsigned long long g = r.env_offset + (unsigned long long)n * r.stride + (unsigned long long)e;
-    uint32_t *obst = const_cast<uint32_t *>(p.obst);
-    uint8_t *goal = const_cast<uint8_t *>(p.goal);
-    int sel = 0;
-    if (lane == 0 && p.navi_alt) sel = __ldcg(p.navi_sel + e);
-    sel = __shfl_sync(MAPF_FULL_MASK, sel, 0);
-    uint32_t *navi = const_cast<uint32_t *>(sel ? p.navi_alt : p.navi);  // the slot's live buffer
-    reset_env_warp<RW, RW>(d, e, r.seed, g, r.density, obst, p.pos, goal, p.steps, p.err);
+#ifdef MAPF_ENABLE_DIAG
+    const unsigned long long tg0 = diag_now();
+#endif
+    reset_env_warp<RW, RW>(d, e, r.seed, g, r.density, const_cast<uint32_t *>(p.obst), p.pos, const_cast<uint8_t *>(p.goal), p.steps,
+                           p.err);
     __threadfence();
     __syncwarp();
-    // get_navi_map (environment.py:195): the same warp-level BFS the load / reset path launches
-    // two agents at a time (one per half warp) for maps of up to 88 cells a side, else one.  (Two interleaved searches per
-    // half warp were measured too: a lone re-generation drops from 272 to 244 us, but the search then runs until the slowest
-    // of FOUR agents is done and votes every third wave -- ~20 % more instructions -- and the rollout with episode handling got
-    // slower, 27.9 -> 30.4 us per step at 2000 steps; profiles/r2_reset_cost.jsonl.)
-    if constexpr (RW <= 3) {
-        // 16 lanes x RPL rows hold the map: RPL = ceil(L / 16)
-        auto pairs = [&](auto rplc) {
-            constexpr int RPL = decltype(rplc)::value;
-            for (int base = 0; base < d.N; base += 2) {
-                const int a = base + (lane >> 4);
-                bfs_navi_warp<RW, RPL, 2>(d, e, a < d.N ? a : 0, 0, a < d.N, obst, goal, navi, nullptr);
-            }
-        };
-        const int rpl = (d.L + 15) >> 4;
-        if constexpr (RW == 1) {
-            if (rpl <= 1) pairs(std::integral_constant<int, 1>{});
-            else pairs(std::integral_constant<int, 2>{});
-        } else if constexpr (RW == 2) {
-            if (rpl <= 2) pairs(std::integral_constant<int, 2>{});
-            else if (rpl == 3) pairs(std::integral_constant<int, 3>{});
-            else pairs(std::integral_constant<int, 4>{});
-        } else {
-            if (rpl <= 4) pairs(std::integral_constant<int, 4>{});
-            else if (rpl == 5) pairs(std::integral_constant<int, 5>{});
-            else pairs(std::integral_constant<int, 6>{});
-        }
+#ifdef MAPF_ENABLE_DIAG
+    gen_ns += diag_now() - tg0;
+#endif
+    const int groups = bfs_groups<RW>(d);
+    if (!r.tq) {
+        for (int grp = 0; grp < groups; ++grp) bfs_group<RW>(p, e, grp);
     } else {
-        constexpr int RPL = 4;  // 32 lanes x 4 rows >= L for every L the RW class admits
-        for (int a = 0; a < d.N; ++a) bfs_navi_warp<RW, RPL, 1>(d, e, a, 0, true, obst, goal, navi, nullptr);
+        // announce the searches ...
+        uint32_t idx = 0;
+        if (lane == 0) idx = atomicAdd(r.tq + 1, 1u);
+        idx = __shfl_sync(MAPF_FULL_MASK, idx, 0);
+        uint32_t *ent = tq_entry(r, idx);
+        if (lane == 0) {
+            ent[2] = 0u;
+            ent[0] = (uint32_t)e;
+            __threadfence();
+            st_release_u32(ent + 1, 0u);
+        }
+        __syncwarp();
+        // ... take part in them, and wait for the ones other warps took
+        int e2, g;
+        while ((g = tq_claim<RW>(p, ent, lane, e2)) >= 0) tq_run<RW>(p, ent, e2, g, lane);
+        unsigned spins = 0;
+        for (;;) {
+            uint32_t fin = 0;
+            if (lane == 0) fin = ld_acquire_u32(ent + 2);
+            fin = __shfl_sync(MAPF_FULL_MASK, fin, 0);
+            if (fin == (uint32_t)groups) break;
+            __nanosleep(200);
+            if (++spins > (1u << 22)) {  // a scheduling bug latches an error instead of hanging the GPU
+                if (lane == 0) atomicOr(p.err, MAPF_ERRBIT_INTERNAL);
+                break;
+            }
+        }
+        if (lane == 0) ent[1] = kTqDone;
     }
     __threadfence();
     __syncwarp();
@@ -261,11 +398,14 @@ rollout_kernel(const __grid_constant__ StepParams p0, const __grid_constant__ Ro
     unsigned nprio = 0;
     if (r.prio) {
         nprio = __ldcg(r.prio);
-        if (nprio * 4u > (unsigned)nenv) nprio = 0;
+        // (pre-generated instances are adopted, not generated here: no long items to hand out first)
+        if (nprio * 4u > (unsigned)nenv || (r.pg_flag && nprio >= (unsigned)r.pregen_min)) nprio = 0;
     }
     const unsigned long long items = (unsigned long long)nprio + (unsigned long long)nenv * (unsigned)r.nchunk;
     bool bulk_used = false;
+    uint32_t visits = 0;
     for (;;) {
+        if (r.tq) tq_help<RW>(p0, r, lane, (uint32_t)(blockIdx.x * WARPS + warp) + 7919u * ++visits);
         unsigned long long it = 0;
         if (lane == 0) it = atomicAdd(r.work, 1ull);
         it = __shfl_sync(MAPF_FULL_MASK, it, 0);
@@ -298,8 +438,15 @@ rollout_kernel(const __grid_constant__ StepParams p0, const __grid_constant__ Ro
             }
             __syncwarp();
         }
+#ifdef MAPF_ENABLE_DIAG
+        const unsigned long long tr_claimed = diag_now();
+        unsigned long long tr_regen = 0, tr_regens = 0, tr_gen = 0;
+#endif
         EnvRegs<K> regs;
         load_env_state<RW, K>(p0, e, lane, s_obst, regs);
+#ifdef MAPF_ENABLE_DIAG
+        const unsigned long long tr_loaded = diag_now();
+#endif
         int sa = t0 % r.action_slots, so = t0 % r.obs_slots, sr = t0 % r.out_slots;
 #pragma unroll
         for (int k = 0; k < K; ++k) {  // the first step's actions; every later step's are requested one step ahead
@@ -326,8 +473,17 @@ rollout_kernel(const __grid_constant__ StepParams p0, const __grid_constant__ Ro
                     int staged = 0;
                     if (r.pg_flag && lane == 0) staged = __ldcg(r.pg_flag + e);
                     staged = __shfl_sync(MAPF_FULL_MASK, staged, 0);
+#ifdef MAPF_ENABLE_DIAG
+                    const unsigned long long tr_a = diag_now();
+#endif
                     if (staged) adopt_pregenerated(p0, r, e);
+#ifdef MAPF_ENABLE_DIAG
+                    else regenerate_env<RW>(p0, r, e, tr_gen);
+                    tr_regen += diag_now() - tr_a;
+                    tr_regens += staged ? 0x10000ull : 1ull;
+#else
                     else regenerate_env<RW>(p0, r, e);
+#endif
                     {
                         int keep[K];   // load_env_state starts a fresh EnvRegs; the prefetched actions stay
 #pragma unroll
@@ -377,6 +533,18 @@ rollout_kernel(const __grid_constant__ StepParams p0, const __grid_constant__ Ro
             if (++so == r.obs_slots) so = 0;
             if (++sr == r.out_slots) sr = 0;
         }
+#ifdef MAPF_ENABLE_DIAG
+        if (r.trace && lane == 0) {
+            const unsigned long long slot = atomicAdd(r.trace, 1ull);
+            if (slot < (unsigned long long)r.trace_cap) {
+                unsigned smid;
+                asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+                unsigned long long *rec = r.trace + 1 + 8 * slot;
+                rec[0] = it, rec[1] = (unsigned long long)e | ((unsigned long long)t0 << 32), rec[2] = tr_claimed, rec[3] = tr_loaded;
+                rec[4] = tr_regen | (tr_gen << 32), rec[5] = tr_regens, rec[6] = diag_now(), rec[7] = smid | ((unsigned long long)(blockIdx.x * WARPS + warp) << 32);
+            }
+        }
+#endif
         if (r.nchunk > 1 && !whole) {
             // publish the chunk: positions / step counter (and a re-generated instance) before the progress word
             __syncwarp();
@@ -394,6 +562,7 @@ rollout_kernel(const __grid_constant__ StepParams p0, const __grid_constant__ Ro
         if (left == (unsigned long long)gridDim.x * WARPS) {
             r.work[0] = 0ull;
             r.work[1] = 0ull;
+            if (r.tq) r.tq[0] = r.tq[1] = 0u;
             __threadfence();
         }
     }

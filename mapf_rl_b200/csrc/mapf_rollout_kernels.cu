@@ -39,7 +39,8 @@ void mapf_set_rollout_tuning(int warps_per_sm, int chunk, int store_mode, int st
 
 bool mapf_rollout_supported(const mapf_env *env) { return env->d.K <= 2; }
 
-// MAPF_ROLLOUT_PREGEN=0 / mapf_debug_rollout_pregen(0): episodes that end inside a rollout launch always re-generate in place
+// MAPF_ROLLOUT_PREGEN / mapf_debug_rollout_pregen: 0 = episodes that end inside a rollout launch always re-generate in place,
+// 1 = pre-generate when at least 16 x SMs environments end in the launch, n > 1 = when at least n do
 int &rollout_pregen_ref()
 {
     static int v = [] {
@@ -49,7 +50,17 @@ int &rollout_pregen_ref()
     return v;
 }
 void mapf_set_rollout_pregen(int on) { rollout_pregen_ref() = on; }
-int mapf_launch_pregen(mapf_env *env, cudaStream_t st);
+#ifdef MAPF_ENABLE_DIAG
+// diagnosis build only: per-item time stamps of the next rollout launches (profiles/tools/r2_rollout_timeline.py)
+static unsigned long long *g_trace = nullptr;
+static int g_trace_cap = 0;
+extern "C" int mapf_diag_rollout_trace(unsigned long long *d_buf, int capacity)
+{
+    g_trace = d_buf, g_trace_cap = capacity;
+    return 0;
+}
+#endif
+int mapf_launch_pregen(mapf_env *env, int min_count, cudaStream_t st);
 
 // The persistent rollout over environments [e0, e1); MAPF_EINVAL = geometry not served (the caller uses chains of launches).
 int mapf_launch_rollout(mapf_env *env, int e0, int e1, int T, const uint8_t *d_actions, int action_slots, uint8_t *d_obs, int obs_slots,
@@ -68,28 +79,36 @@ int mapf_launch_rollout(mapf_env *env, int e0, int e1, int T, const uint8_t *d_a
     r.max_steps = env->ar_max_steps;
     r.seed = env->ar_seed, r.env_offset = env->ar_offset, r.stride = env->ar_stride, r.density = env->ar_density;
     r.episode = env->ro_episode;
+#ifdef MAPF_ENABLE_DIAG
+    r.trace = g_trace, r.trace_cap = g_trace_cap;
+#endif
     static const int use_prio = [] { const char *v = std::getenv("MAPF_ROLLOUT_PRIO"); return v ? std::atoi(v) : 1; }();
     r.prio = nullptr, r.prio_flag = nullptr, r.pg_flag = nullptr;
+    r.tq = nullptr;
     if (r.max_steps > 0) {
-        // the environments that hit the cap inside this launch are known up front (rollout_prio_kernel) ...
+        static const int use_tq = [] { const char *v = std::getenv("MAPF_ROLLOUT_TASKS"); return v ? std::atoi(v) : 1; }();
+        if (use_tq) r.tq = env->ro_tq, r.tq_cap = env->ro_tq_cap;
+        // The environments that hit the cap inside this launch are known up front (rollout_prio_kernel).  MANY of them: their
+        // next instances are generated now, by the dedicated generator / BFS kernels at full occupancy, into the staging arrays
+        // and the second heuristic-map buffer, and the rollout kernel adopts them at the episode's end.  FEW (the dedicated
+        // kernels would be latency-bound: a lone generator takes ~130 us): they re-generate inside the rollout kernel, are
+        // its long items and are handed out first.  The count is only known on the device: both the pre-generation kernels
+        // and the rollout kernel compare it with pregen_min.
         const bool pregen = rollout_pregen_ref() != 0 && env->navi_alt != nullptr;
-        const bool prio = use_prio && !pregen && T <= r.max_steps / 2;
+        const bool prio = use_prio && T <= r.max_steps / 2;
         if (pregen || prio) {
             rollout_prio_kernel<<<1, 1024, 0, st>>>(env->steps, e0, e1, T, r.max_steps, env->ro_prio, env->ro_prio_flag, env->pg_flag,
                                                     env->ro_work);
             MAPF_CUDA(cudaGetLastError());
         }
+        r.pregen_min = rollout_pregen_ref() > 1 ? rollout_pregen_ref() : env->num_sms * 16;
         if (pregen) {
-            // ... their next instances are generated now, by the dedicated generator / BFS kernels at full occupancy, into the
-            // staging arrays and the second heuristic-map buffer; the rollout kernel adopts them at the episode's end
-            const int rc = mapf_launch_pregen(env, st);
+            const int rc = mapf_launch_pregen(env, r.pregen_min, st);
             if (rc != MAPF_OK) return rc;
             r.pg_flag = env->pg_flag, r.pg_obst = env->pg_obst, r.pg_pos = env->pg_pos, r.pg_goal = env->pg_goal;
             r.navi_sel = env->navi_sel;
-        } else if (prio) {
-            // ... or, without the staging memory, they are the long items of the launch and are handed out first
-            r.prio = env->ro_prio, r.prio_flag = env->ro_prio_flag;
         }
+        if (prio) r.prio = env->ro_prio, r.prio_flag = env->ro_prio_flag;
     }
     // occupancy class: the smallest one that holds the requested warps
     const RolloutTuning &tn = rollout_tuning();
