@@ -230,12 +230,13 @@ int mapf_debug_step_tuning(int32_t variant, int32_t flags, int32_t ctas_per_sm);
  * Read once from MAPF_ROLLOUT_PERSISTENT / _WARPS_PER_SM / _CHUNK / _STORE_MODE / _STAGGER_NS. */
 int mapf_debug_rollout_tuning(int32_t persistent, int32_t warps_per_sm, int32_t chunk, int32_t store_mode, int32_t stagger_ns);
 /* Episode handling of mapf_env_rollout (mapf_env_set_autoreset).  The environments whose episode ends at the step cap inside
- * a launch are known before it.  on = 1 (default): when at least 16 x SMs of them do, their next instances are generated
- * BEFORE the launch by the dedicated generator / BFS kernels (full occupancy) and the rollout kernel adopts them at the
- * episode's end; fewer are re-generated inside the rollout kernel (generator by the environment's warp, the per-agent
- * searches as tasks any warp takes) -- the dedicated kernels would be latency-bound.  on = n > 1: the threshold is n
- * environments; 0: always inside the kernel; < 0 only queries.  Read once from MAPF_ROLLOUT_PREGEN.  Every form produces
- * the same instances (a second episode end of an environment in one launch is always handled inside the kernel). */
+ * a launch are known before it, and their next instances can be generated ahead by the dedicated generator / BFS kernels and
+ * adopted by the rollout kernel at the episode's end.  mode 1 (default) = automatic: BEFORE the launch when many are due
+ * (the kernels run at full occupancy), BESIDE it on a second stream when few are (the kernels are latency-bound then);
+ * 2 = always before; 3 = always beside; 0 = never: every episode end re-generates inside the rollout kernel (generator by the
+ * environment's warp, the per-agent searches as tasks any warp takes), which is also what happens when a staged instance
+ * is not ready in time and for a second episode end of an environment in one launch; < 0 only queries.  Read once from
+ * MAPF_ROLLOUT_PREGEN.  Every form produces the same instances. */
 int mapf_debug_rollout_pregen(int32_t on);
 /* Selects the form of mapf_env_step_host (0..4, see mapf_abi.cu; < 0 only queries); returns the mode in force. */
 int mapf_debug_step_host_mode(int32_t mode);

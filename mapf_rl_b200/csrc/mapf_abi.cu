@@ -192,7 +192,9 @@ int mapf_env_create(const mapf_env_config *cfg, mapf_env **out)
     if (rc == MAPF_OK) rc = dev_alloc(&env->steps, (size_t)d.B, &total);
     if (rc == MAPF_OK) rc = dev_alloc(&env->err, 1, &total);
     if (rc == MAPF_OK) rc = dev_alloc(&env->navi_sel, (size_t)d.B, &total);
-    if (rc == MAPF_OK) rc = dev_alloc(&env->pg_flag, (size_t)d.B, &total);
+    if (rc == MAPF_OK) rc = dev_alloc(&env->pg_epi, (size_t)d.B, &total);
+    if (rc == MAPF_OK) rc = dev_alloc(&env->pg_n, (size_t)d.B, &total);
+    if (rc == MAPF_OK) rc = dev_alloc(&env->pg_cnt, (size_t)d.B, &total);
     if (rc == MAPF_OK) rc = dev_alloc(&env->ro_work, 4, &total);
     if (rc == MAPF_OK) rc = dev_alloc(&env->ro_progress, (size_t)d.B, &total);
     if (rc == MAPF_OK) rc = dev_alloc(&env->ro_episode, (size_t)d.B, &total);
@@ -206,7 +208,9 @@ int mapf_env_create(const mapf_env_config *cfg, mapf_env **out)
         if (e2 == cudaSuccess) e2 = cudaMemset(env->ro_tq, 0x80, ((size_t)env->ro_tq_cap * 4 + 4) * 4);  // every entry free
         if (e2 == cudaSuccess) e2 = cudaMemset(env->ro_tq, 0, 16);
         if (e2 == cudaSuccess) e2 = cudaMemset(env->navi_sel, 0, (size_t)d.B);
-        if (e2 == cudaSuccess) e2 = cudaMemset(env->pg_flag, 0, (size_t)d.B);
+        if (e2 == cudaSuccess) e2 = cudaMemset(env->pg_epi, 0, (size_t)d.B * 4);
+        if (e2 == cudaSuccess) e2 = cudaMemset(env->pg_n, 0, (size_t)d.B * 4);
+        if (e2 == cudaSuccess) e2 = cudaMemset(env->pg_cnt, 0, (size_t)d.B * 4);
         if (e2 == cudaSuccess) e2 = cudaMemset(env->ro_progress, 0, (size_t)d.B * 4);
         if (e2 == cudaSuccess) e2 = cudaMemset(env->ro_episode, 0, (size_t)d.B * 4);
         if (e2 == cudaSuccess) e2 = cudaMemset(env->pos, 0, BN * 2);
@@ -240,7 +244,12 @@ int mapf_env_destroy(mapf_env *env)
     cudaFree(env->pg_pos);
     cudaFree(env->pg_goal);
     cudaFree(env->pg_steps);
-    cudaFree(env->pg_flag);
+    cudaFree(env->pg_epi);
+    cudaFree(env->pg_n);
+    cudaFree(env->pg_cnt);
+    if (env->pg_stream) cudaStreamDestroy(env->pg_stream);
+    if (env->pg_fork) cudaEventDestroy(env->pg_fork);
+    if (env->pg_join) cudaEventDestroy(env->pg_join);
     cudaFree(env->steps);
     cudaFree(env->err);
     cudaFree(env->ro_work);
@@ -623,7 +632,7 @@ int mapf_env_set_autoreset(mapf_env *env, int32_t max_steps, uint64_t seed, uint
     env->ar_seed = seed, env->ar_offset = env_offset, env->ar_stride = stride ? stride : (uint64_t)env->d.B;
     env->ar_density = density;
     MAPF_CUDA(cudaMemsetAsync(env->ro_episode, 0, (size_t)env->d.B * 4, static_cast<cudaStream_t>(stream)));
-    MAPF_CUDA(cudaMemsetAsync(env->pg_flag, 0, (size_t)env->d.B, static_cast<cudaStream_t>(stream)));
+    MAPF_CUDA(cudaMemsetAsync(env->pg_epi, 0, (size_t)env->d.B * 4, static_cast<cudaStream_t>(stream)));
     if (max_steps > 0 && !env->navi_alt) {
         // the second heuristic-map buffer and the staging of pre-generated instances (mapf_common.cuh).  Without the memory
         // for them episodes are still handled, by re-generating inside the rollout kernel.

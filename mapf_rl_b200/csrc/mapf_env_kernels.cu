@@ -126,10 +126,11 @@ bfs_navi_kernel(EnvDims d, const int32_t *__restrict__ env_ids, const uint8_t *_
 // the staged obstacle bitmaps / goals, writes the buffer the slot's live instance does not use.  The list's length is only
 // known on the device, so a fixed grid claims (slot, agent group) items from a counter.
 template <int RW, int RPL, int APW>
-__global__ void __launch_bounds__(kBfsWarps * 32, RW * RPL <= 9 ? 8 : 1)
+__global__ void __launch_bounds__(kBfsWarps * 32, RW * RPL <= 9 ? 8 : 4)
 pregen_bfs_kernel(EnvDims d, const uint32_t *__restrict__ list, int min_count, unsigned long long *__restrict__ counter,
                   const uint32_t *__restrict__ pg_obst, const uint8_t *__restrict__ pg_goal, uint32_t *__restrict__ navi,
-                  uint32_t *__restrict__ navi_alt, const uint8_t *__restrict__ navi_sel)
+                  uint32_t *__restrict__ navi_alt, const uint8_t *__restrict__ navi_sel, const uint32_t *__restrict__ pg_n,
+                  uint32_t *__restrict__ pg_cnt, uint32_t *__restrict__ pg_epi)
 {
     constexpr int LW = 32 / APW;
     const int lane = lane_id();
@@ -145,8 +146,17 @@ pregen_bfs_kernel(EnvDims d, const uint32_t *__restrict__ list, int min_count, u
         const int a = (int)(it - (unsigned long long)i * groups) * APW + lane / LW;
         const int e = (int)list[1 + i];
         const bool alive = a < d.N;
-        uint32_t *nv = navi_sel[e] ? navi : navi_alt;
+        // (the slot's selector only changes when THIS instance is adopted, i.e. after the last group has published it)
+        uint32_t *nv = __ldcg(navi_sel + e) ? navi : navi_alt;
         bfs_navi_warp<RW, RPL, APW>(d, e, alive ? a : 0, 0, alive, pg_obst, pg_goal, nv, nullptr);
+        __syncwarp();
+        if (lane == 0) {
+            __threadfence();  // the tiles (and, through the generator's launch, the staged state) before the count
+            if (atomicAdd(pg_cnt + e, 1u) + 1u == groups) {
+                __threadfence();
+                asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(pg_epi + e), "r"(__ldcg(pg_n + e)) : "memory");
+            }
+        }
     }
 }
 
@@ -277,7 +287,8 @@ static int launch_bfs_rw(mapf_env *env, const int32_t *ids, const uint8_t *mask,
     do {                                                                                                                            \
         if (pregen)                                                                                                                 \
             pregen_bfs_kernel<RW, RPL, APW><<<grid, kBfsWarps * 32, 0, st>>>(d, env->ro_prio, pregen_min, env->ro_work + 3, env->pg_obst, \
-                                                                             env->pg_goal, env->navi, env->navi_alt, env->navi_sel); \
+                                                                             env->pg_goal, env->navi, env->navi_alt, env->navi_sel, \
+                                                                             env->pg_n, env->pg_cnt, env->pg_epi);                   \
         else                                                                                                                        \
             bfs_navi_kernel<RW, RPL, APW><<<grid, kBfsWarps * 32, 0, st>>>(d, ids, mask, n, env->obst, env->goal, env->navi,         \
                                                                            env->navi_alt, env->navi_sel, dist);                      \

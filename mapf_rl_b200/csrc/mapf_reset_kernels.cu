@@ -26,7 +26,7 @@ __global__ void __launch_bounds__(128)
 pregen_reset_kernel(EnvDims d, const uint32_t *__restrict__ list, int min_count, unsigned long long *__restrict__ counter, uint64_t seed,
                     uint64_t env_offset, uint64_t stride, float density, const uint32_t *__restrict__ episode,
                     uint32_t *__restrict__ pg_obst, uint8_t *__restrict__ pg_pos, uint8_t *__restrict__ pg_goal,
-                    int32_t *__restrict__ pg_steps, uint8_t *__restrict__ pg_flag, int32_t *__restrict__ err)
+                    int32_t *__restrict__ pg_steps, uint32_t *__restrict__ pg_n, int32_t *__restrict__ err)
 {
     const int lane = threadIdx.x & 31;
     const unsigned long long count = list[0];
@@ -37,9 +37,12 @@ pregen_reset_kernel(EnvDims d, const uint32_t *__restrict__ list, int min_count,
         it = __shfl_sync(MAPF_FULL_MASK, it, 0);
         if (it >= count) break;
         const int e = (int)list[1 + it];
-        const uint64_t g = env_offset + (uint64_t)(episode[e] + 1u) * stride + (uint64_t)e;
+        // (__ldcg: beside a running rollout kernel the slot's episode count may just have moved on -- a done-triggered episode
+        // end -- and the instance staged here is then simply never adopted)
+        const uint32_t n = __ldcg(episode + e) + 1u;
+        const uint64_t g = env_offset + (uint64_t)n * stride + (uint64_t)e;
         reset_env_warp<RW, RPL>(d, e, seed, g, density, pg_obst, pg_pos, pg_goal, pg_steps, err);
-        if (lane == 0) pg_flag[e] = 1;
+        if (lane == 0) pg_n[e] = n;
     }
 }
 
@@ -57,7 +60,7 @@ int launch_reset_rw(mapf_env *env, const uint8_t *mask, uint64_t seed, uint64_t 
             pregen_reset_kernel<RW, RPL><<<grid, warps * 32, 0, st>>>(d, env->ro_prio, pregen_min, env->ro_work + 2, env->ar_seed, \
                                                                       env->ar_offset, env->ar_stride, env->ar_density,           \
                                                                       env->ro_episode, env->pg_obst, env->pg_pos, env->pg_goal,  \
-                                                                      env->pg_steps, env->pg_flag, env->err);                    \
+                                                                      env->pg_steps, env->pg_n, env->err);                       \
         else                                                                                                                     \
             reset_kernel<RW, RPL><<<grid, warps * 32, 0, st>>>(d, mask, seed, off, density, env->obst, env->pos, env->goal,      \
                                                                 env->steps, env->err);                                           \

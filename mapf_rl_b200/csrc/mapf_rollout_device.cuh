@@ -57,7 +57,8 @@ struct RolloutArgs {
     const uint32_t *prio;    // [0] count, [1 ..] environment ids
     const uint8_t *prio_flag;  // [B]
     // pre-generated next instances (mapf_launch_pregen; NULL: every episode end re-generates in place)
-    uint8_t *pg_flag;        // [B] 1: staged
+    uint32_t *pg_epi;        // [B] episode number of the slot's staged instance (0: none), see mapf_env
+    int prio_last;           // the listed environments are handed out LAST (their instances are being staged beside this launch)
     const uint32_t *pg_obst;
     const uint8_t *pg_pos, *pg_goal;
     uint8_t *navi_sel;       // [B]
@@ -85,7 +86,8 @@ __device__ __forceinline__ unsigned long long diag_now()
 // over all T steps; the rest of the batch follows as time-major chunks and fills in around them.  Without this the last
 // re-generations start late and the launch ends with a tail of a few warps.  One CTA (the scan is B loads).
 __global__ void rollout_prio_kernel(const int32_t *__restrict__ steps, int e0, int e1, int T, int cap, uint32_t *__restrict__ prio,
-                                    uint8_t *__restrict__ prio_flag, uint8_t *__restrict__ pg_flag, unsigned long long *__restrict__ work)
+                                    uint8_t *__restrict__ prio_flag, uint32_t *__restrict__ pg_epi, uint32_t *__restrict__ pg_cnt,
+                                    unsigned long long *__restrict__ work)
 {
     __shared__ unsigned count;
     if (threadIdx.x == 0) {
@@ -96,7 +98,8 @@ __global__ void rollout_prio_kernel(const int32_t *__restrict__ steps, int e0, i
     for (int e = e0 + threadIdx.x; e < e1; e += blockDim.x) {
         const bool will = steps[e] + T > cap;
         prio_flag[e] = will ? 1 : 0;
-        pg_flag[e] = 0;  // set by pregen_reset_kernel once the slot's next instance is staged
+        pg_epi[e] = 0;   // published by pregen_bfs_kernel once the slot's next instance is staged
+        pg_cnt[e] = 0;
         if (will) prio[1 + atomicAdd(&count, 1u)] = (uint32_t)e;
     }
     __syncthreads();
@@ -355,7 +358,7 @@ __device__ __forceinline__ void adopt_pregenerated(const StepParams &p, const Ro
         p.steps[e] = 0;
         r.episode[e] = __ldcg(r.episode + e) + 1;
         r.navi_sel[e] = __ldcg(r.navi_sel + e) ^ 1;
-        r.pg_flag[e] = 0;
+        r.pg_epi[e] = 0;
     }
     __threadfence();
     __syncwarp();
@@ -399,7 +402,7 @@ rollout_kernel(const __grid_constant__ StepParams p0, const __grid_constant__ Ro
     if (r.prio) {
         nprio = __ldcg(r.prio);
         // (pre-generated instances are adopted, not generated here: no long items to hand out first)
-        if (nprio * 4u > (unsigned)nenv || (r.pg_flag && nprio >= (unsigned)r.pregen_min)) nprio = 0;
+        if (nprio * 4u > (unsigned)nenv || (r.pg_epi && !r.prio_last && nprio >= (unsigned)r.pregen_min)) nprio = 0;
     }
     const unsigned long long items = (unsigned long long)nprio + (unsigned long long)nenv * (unsigned)r.nchunk;
     bool bulk_used = false;
@@ -412,12 +415,14 @@ rollout_kernel(const __grid_constant__ StepParams p0, const __grid_constant__ Ro
         if (it >= items) break;
         int k, e, t0, t1;
         bool whole = false;
-        if (it < nprio) {
-            e = (int)__ldcg(r.prio + 1 + it);
+        const unsigned long long first_regular = r.prio_last ? 0ull : (unsigned long long)nprio;
+        const unsigned long long first_prio = r.prio_last ? items - nprio : 0ull;
+        if (it >= first_prio && it < first_prio + nprio) {
+            e = (int)__ldcg(r.prio + 1 + (it - first_prio));
             k = 0, t0 = 0, t1 = r.T;
             whole = true;
         } else {
-            const unsigned long long j = it - nprio;
+            const unsigned long long j = it - first_regular;
             k = (int)(j / (unsigned)nenv);
             e = p0.env_begin + (int)(j - (unsigned long long)k * (unsigned)nenv);
             if (nprio && __ldcg(r.prio_flag + e)) continue;  // taken as a priority item
@@ -471,7 +476,10 @@ rollout_kernel(const __grid_constant__ StepParams p0, const __grid_constant__ Ro
                 const int st = __shfl_sync(MAPF_FULL_MASK, regs.step, 0);
                 if (regs.finished || st >= r.max_steps) {
                     int staged = 0;
-                    if (r.pg_flag && lane == 0) staged = __ldcg(r.pg_flag + e);
+                    if (r.pg_epi && lane == 0) {
+                        const uint32_t have = ld_acquire_u32(r.pg_epi + e);
+                        staged = have != 0 && have == __ldcg(r.episode + e) + 1u;
+                    }
                     staged = __shfl_sync(MAPF_FULL_MASK, staged, 0);
 #ifdef MAPF_ENABLE_DIAG
                     const unsigned long long tr_a = diag_now();
@@ -573,6 +581,7 @@ struct RolloutTuning {
     int chunk;         // steps per work item (0 = automatic)
     int store_mode;    // 0 direct, 1 bulk
     int stagger_ns;
+    int reserve_ctas;  // resident CTA slots per SM left to kernels that run beside the launch
 };
 
 // MINB = resident CTAs (of 2 warps) per SM the kernel is compiled for: 8 -> 128 registers per thread, 12 -> 85, 16 -> 64
@@ -603,6 +612,7 @@ int launch_rollout_cfg(mapf_env *env, const StepParams &p, RolloutArgs r, const 
         env->ro_key = key;
     }
     int ctas_per_sm = env->ro_per_sm;
+    if (tn.reserve_ctas > 0 && ctas_per_sm > tn.reserve_ctas) ctas_per_sm -= tn.reserve_ctas;
     const int want = ((tn.warps_per_sm > 0 ? tn.warps_per_sm : MINB * WARPS) + WARPS - 1) / WARPS;
     if (ctas_per_sm > want) ctas_per_sm = want;
     const int nenv = p.env_end - p.env_begin;

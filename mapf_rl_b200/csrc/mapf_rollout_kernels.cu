@@ -16,7 +16,7 @@ namespace {
 RolloutTuning &rollout_tuning()
 {
     static RolloutTuning t = [] {
-        RolloutTuning r{0, 0, 0, 1000};
+        RolloutTuning r{0, 0, 0, 1000, 0};
         if (const char *s = std::getenv("MAPF_ROLLOUT_WARPS_PER_SM")) r.warps_per_sm = std::atoi(s);
         if (const char *s = std::getenv("MAPF_ROLLOUT_CHUNK")) r.chunk = std::atoi(s);
         if (const char *s = std::getenv("MAPF_ROLLOUT_STORE_MODE")) r.store_mode = std::atoi(s);
@@ -40,7 +40,7 @@ void mapf_set_rollout_tuning(int warps_per_sm, int chunk, int store_mode, int st
 bool mapf_rollout_supported(const mapf_env *env) { return env->d.K <= 2; }
 
 // MAPF_ROLLOUT_PREGEN / mapf_debug_rollout_pregen: 0 = episodes that end inside a rollout launch always re-generate in place,
-// 1 = pre-generate when at least 16 x SMs environments end in the launch, n > 1 = when at least n do
+// 1 = automatic, 2 = pre-generate before the launch, 3 = pre-generate beside the launch (see mapf_launch_rollout)
 int &rollout_pregen_ref()
 {
     static int v = [] {
@@ -83,40 +83,83 @@ int mapf_launch_rollout(mapf_env *env, int e0, int e1, int T, const uint8_t *d_a
     r.trace = g_trace, r.trace_cap = g_trace_cap;
 #endif
     static const int use_prio = [] { const char *v = std::getenv("MAPF_ROLLOUT_PRIO"); return v ? std::atoi(v) : 1; }();
-    r.prio = nullptr, r.prio_flag = nullptr, r.pg_flag = nullptr;
+    r.prio = nullptr, r.prio_flag = nullptr, r.pg_epi = nullptr, r.prio_last = 0;
     r.tq = nullptr;
+    int reserve_ctas = 0;
     if (r.max_steps > 0) {
         static const int use_tq = [] { const char *v = std::getenv("MAPF_ROLLOUT_TASKS"); return v ? std::atoi(v) : 1; }();
         if (use_tq) r.tq = env->ro_tq, r.tq_cap = env->ro_tq_cap;
-        // The environments that hit the cap inside this launch are known up front (rollout_prio_kernel).  MANY of them: their
-        // next instances are generated now, by the dedicated generator / BFS kernels at full occupancy, into the staging arrays
-        // and the second heuristic-map buffer, and the rollout kernel adopts them at the episode's end.  FEW (the dedicated
-        // kernels would be latency-bound: a lone generator takes ~130 us): they re-generate inside the rollout kernel, are
-        // its long items and are handed out first.  The count is only known on the device: both the pre-generation kernels
-        // and the rollout kernel compare it with pregen_min.
-        const bool pregen = rollout_pregen_ref() != 0 && env->navi_alt != nullptr;
+        // The environments that hit the cap inside this launch are known up front (rollout_prio_kernel), and their next
+        // instances can be generated ahead by the dedicated generator / BFS kernels into the staging arrays and the second
+        // heuristic-map buffer; the rollout kernel adopts them at the episode's end.
+        //  * MANY are due (the estimate B * T / cap reaches 16 x SMs): the dedicated kernels run at full occupancy BEFORE the
+        //    rollout kernel, on the same stream (C4, 80x80 / 64 agents / cap 32: 279 -> 155 us per step).
+        //  * FEW: the dedicated kernels would be latency-bound (a lone generator takes ~130 us: +190 us in front of a 430-us
+        //    launch at C2), so the episodes re-generate inside the rollout kernel -- generator by the slot's warp, searches as
+        //    tasks -- and the listed environments, its long items, are handed out first.
+        //  * (mode 3, not automatic) BESIDE the rollout kernel on a high-priority stream: the rollout kernel leaves CTA slots
+        //    free, hands the listed environments out LAST and adopts an instance only if it has been published by then.  It
+        //    moves the same work to other warps and takes slots from the store stream while it runs: C3 57.4 -> 51.7 us per step,
+        //    but C2 28.9 -> 30 us (two slots per SM reserved) or 41 us (one slot: the instances are late, every episode end
+        //    re-generates at the end of the launch); profiles/r2_rollout_timeline_beside.jsonl.
+        // The true count is only known on the device; the estimate picks the form, never the result.
+        const int mode = rollout_pregen_ref();   // 0 off, 1 automatic, 2 always before, 3 always beside
+        const bool have_mem = env->navi_alt != nullptr;
+        cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+        MAPF_CUDA(cudaStreamIsCapturing(st, &cap));
+        const long long due = (long long)(e1 - e0) * (T < r.max_steps ? T : r.max_steps) / r.max_steps;
+        bool before = false, beside = false;
+        if (have_mem && mode != 0) {
+            if (mode == 2) before = true;
+            else if (mode == 3) beside = true;
+            else if (due >= (long long)env->num_sms * 16) before = true;
+            if (beside && cap != cudaStreamCaptureStatusNone) beside = false;  // (a captured launch re-generates in place)
+        }
         const bool prio = use_prio && T <= r.max_steps / 2;
-        if (pregen || prio) {
-            rollout_prio_kernel<<<1, 1024, 0, st>>>(env->steps, e0, e1, T, r.max_steps, env->ro_prio, env->ro_prio_flag, env->pg_flag,
-                                                    env->ro_work);
+        if (before || beside || prio) {
+            rollout_prio_kernel<<<1, 1024, 0, st>>>(env->steps, e0, e1, T, r.max_steps, env->ro_prio, env->ro_prio_flag, env->pg_epi,
+                                                    env->pg_cnt, env->ro_work);
             MAPF_CUDA(cudaGetLastError());
         }
-        r.pregen_min = rollout_pregen_ref() > 1 ? rollout_pregen_ref() : env->num_sms * 16;
-        if (pregen) {
-            const int rc = mapf_launch_pregen(env, r.pregen_min, st);
+        r.pregen_min = 0;
+        if (before) {
+            const int rc = mapf_launch_pregen(env, 0, st);
             if (rc != MAPF_OK) return rc;
-            r.pg_flag = env->pg_flag, r.pg_obst = env->pg_obst, r.pg_pos = env->pg_pos, r.pg_goal = env->pg_goal;
+        } else if (beside) {
+            if (!env->pg_stream) {
+                int lo = 0, hi = 0;
+                MAPF_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+                MAPF_CUDA(cudaStreamCreateWithPriority(&env->pg_stream, cudaStreamNonBlocking, hi));
+                MAPF_CUDA(cudaEventCreateWithFlags(&env->pg_fork, cudaEventDisableTiming));
+                MAPF_CUDA(cudaEventCreateWithFlags(&env->pg_join, cudaEventDisableTiming));
+            }
+            MAPF_CUDA(cudaEventRecord(env->pg_fork, st));
+            MAPF_CUDA(cudaStreamWaitEvent(env->pg_stream, env->pg_fork, 0));
+            const int rc = mapf_launch_pregen(env, 0, env->pg_stream);
+            if (rc != MAPF_OK) return rc;
+            MAPF_CUDA(cudaEventRecord(env->pg_join, env->pg_stream));
+            r.prio_last = 1;
+            static const int reserve = [] { const char *v = std::getenv("MAPF_ROLLOUT_RESERVE"); return v ? std::atoi(v) : 1; }();
+            reserve_ctas = reserve;
+        }
+        if (before || beside) {
+            r.pg_epi = env->pg_epi, r.pg_obst = env->pg_obst, r.pg_pos = env->pg_pos, r.pg_goal = env->pg_goal;
             r.navi_sel = env->navi_sel;
         }
-        if (prio) r.prio = env->ro_prio, r.prio_flag = env->ro_prio_flag;
+        if (prio || beside) r.prio = env->ro_prio, r.prio_flag = env->ro_prio_flag;
     }
     // occupancy class: the smallest one that holds the requested warps
     const RolloutTuning &tn = rollout_tuning();
     const int want = tn.warps_per_sm > 0 ? tn.warps_per_sm : 16;  // measured: 16 register-rich warps beat 24 / 32 leaner ones, with and without episode handling (profiles/r2_rollout_sweep.jsonl)
     RolloutTuning use = tn;
     use.warps_per_sm = want;
-    if (want <= 16) return mapf_launch_rollout_occ8(env, p, &r, &use, st);
-    if (want <= 20) return mapf_launch_rollout_occ10(env, p, &r, &use, st);
-    if (want <= 24) return mapf_launch_rollout_occ12(env, p, &r, &use, st);
-    return mapf_launch_rollout_occ16(env, p, &r, &use, st);
+    use.reserve_ctas = reserve_ctas;
+    int rc;
+    if (want <= 16) rc = mapf_launch_rollout_occ8(env, p, &r, &use, st);
+    else if (want <= 20) rc = mapf_launch_rollout_occ10(env, p, &r, &use, st);
+    else if (want <= 24) rc = mapf_launch_rollout_occ12(env, p, &r, &use, st);
+    else rc = mapf_launch_rollout_occ16(env, p, &r, &use, st);
+    // the pre-generation beside the launch joins the caller's stream (it also has to be over before the next launch's list)
+    if (r.prio_last) MAPF_CUDA(cudaStreamWaitEvent(st, env->pg_join, 0));
+    return rc;
 }

@@ -389,15 +389,16 @@ def test_rollout_full_size_c3_c4_vs_oracle(rollout_tuning, B, N, L, name):
 
 @pytest.mark.parametrize("B,N,L,cap,chunk,store", [(300, 1, 6, 9, 0, 0), (257, 2, 7, 6, 3, 1), (600, 8, 12, 5, 4, 0),
                                                      (96, 32, 40, 4, 2, 1), (40, 64, 40, 3, 5, 0), (24, 40, 64, 4, 0, 0)])
-@pytest.mark.parametrize("pregen", [2, 0])
+@pytest.mark.parametrize("pregen", [2, 3, 0])
 def test_rollout_autoreset_vs_twin(rollout_tuning, B, N, L, cap, chunk, store, pregen):
     """Episode handling inside the launch (worker.py:390,422-428): a step that finds its environment finished -- all agents
     on their goals after the previous step (tiny boards reach that within a few random steps), or `cap` steps taken --
     re-generates the slot and emits the first observation.  The twin does the same through the public pieces:
     reset(mask, env_offset = base + n * stride) + observe, else step.
-    pregen = 2 (two or more slots due in the launch): the first episode end of a slot in a launch adopts an instance staged by
-    the dedicated generator / BFS kernels before the launch (double-buffered heuristic maps), later ones re-generate inside
-    the kernel -- generator by the slot's warp, the per-agent searches as tasks any warp takes; 0: always inside."""
+    pregen = 2: the first episode end of a slot in a launch adopts an instance staged by the dedicated generator / BFS kernels
+    BEFORE the launch (double-buffered heuristic maps), later ones re-generate inside the kernel -- generator by the slot's
+    warp, the per-agent searches as tasks any warp takes; 3: staged BESIDE the launch on a second stream (adopted if ready in
+    time); 0: always inside."""
     import torch
     from mapf_rl_b200 import _native
     T, A = 23, 5
