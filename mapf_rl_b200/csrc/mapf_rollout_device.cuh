@@ -330,7 +330,19 @@ __device__ __noinline__ void regenerate_env(const StepParams &p, const RolloutAr
                 break;
             }
         }
-        if (lane == 0) ent[1] = kTqDone;
+        if (lane == 0) {
+            ent[1] = kTqDone;
+            // move the head hint over the complete entries at the front (helpers pick among [head, tail))
+            __threadfence();
+            uint32_t h = __ldcg(r.tq);
+            const uint32_t t = __ldcg(r.tq + 1);
+            while ((int32_t)(t - h) > 0) {
+                const int32_t c = (int32_t)__ldcg(tq_entry(r, h) + 1);
+                if (c >= 0 || c < (int32_t)0xA0000000u) break;  // open, or reserved and not published yet
+                ++h;
+            }
+            atomicMax(r.tq, h);
+        }
     }
     __threadfence();
     __syncwarp();
