@@ -238,6 +238,9 @@ int mapf_debug_rollout_tuning(int32_t persistent, int32_t warps_per_sm, int32_t 
  * is not ready in time and for a second episode end of an environment in one launch; < 0 only queries.  Read once from
  * MAPF_ROLLOUT_PREGEN.  Every form produces the same instances. */
 int mapf_debug_rollout_pregen(int32_t on);
+/* In-launch re-generations announce their per-agent searches as tasks any warp of the rollout kernel takes (1) or run them
+ * all on the environment's own warp (0, default); < 0 only queries.  Read once from MAPF_ROLLOUT_TASKS.  Same instances. */
+int mapf_debug_rollout_tasks(int32_t on);
 /* Selects the form of mapf_env_step_host (0..4, see mapf_abi.cu; < 0 only queries); returns the mode in force. */
 int mapf_debug_step_host_mode(int32_t mode);
 

@@ -76,6 +76,7 @@ SIGNATURES = {
     "mapf_debug_step_host_mode": (C.c_int, [_i32]),
     "mapf_debug_rollout_tuning": (C.c_int, [_i32, _i32, _i32, _i32, _i32]),
     "mapf_debug_rollout_pregen": (C.c_int, [_i32]),
+    "mapf_debug_rollout_tasks": (C.c_int, [_i32]),
     "mapf_env_comm_mask": (C.c_int, [_vp, _i32, _vp, _vp]),
     "mapf_env_get_state": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "mapf_env_set_state": (C.c_int, [_vp, _vp, _vp, _vp]),

@@ -21,6 +21,8 @@ bool mapf_rollout_supported(const mapf_env *);
 void mapf_set_rollout_tuning(int, int, int, int);
 void mapf_set_rollout_pregen(int);
 int &rollout_pregen_ref();
+void mapf_set_rollout_tasks(int);
+int &rollout_tasks_ref();
 void mapf_set_step_tuning(int, int, int);
 int mapf_step_tuning_generation();
 int mapf_launch_unpack(mapf_env *, uint8_t *, uint8_t *, cudaStream_t);
@@ -942,6 +944,12 @@ int mapf_debug_rollout_pregen(int32_t on)
 {
     if (on >= 0) mapf_set_rollout_pregen(on);
     return rollout_pregen_ref();
+}
+
+int mapf_debug_rollout_tasks(int32_t on)
+{
+    if (on >= 0) mapf_set_rollout_tasks(on);
+    return rollout_tasks_ref();
 }
 
 int mapf_debug_step_host_mode(int32_t mode)

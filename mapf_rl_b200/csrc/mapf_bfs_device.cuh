@@ -103,10 +103,13 @@ __device__ __forceinline__ void bfs_apply(BfsState<RW, RPL> &S, const uint32_t (
     for (int q = 0; q < RPL; ++q)
 #pragma unroll
         for (int w = 0; w < RW; ++w) {
-            S.unv[q][w] &= ~nw[q][w];
+            // nw is a subset of unv and disjoint from the residue planes: clearing / setting its bits is a subtraction / an
+            // addition, which the compiler can place on the FMA pipe (IMAD.IADD) -- the search is bound by the ALU pipe
+            // (LOP3 / SHF at half rate: ncu math-pipe throttle), the FMA pipe is idle
+            S.unv[q][w] -= nw[q][w];
             S.fro[q][w] = nw[q][w];
-            if constexpr (SEL == 1) S.m1[q][w] |= nw[q][w];
-            if constexpr (SEL == 2) S.m2[q][w] |= nw[q][w];
+            if constexpr (SEL == 1) S.m1[q][w] += nw[q][w];
+            if constexpr (SEL == 2) S.m2[q][w] += nw[q][w];
         }
 }
 

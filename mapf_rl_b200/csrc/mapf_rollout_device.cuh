@@ -163,16 +163,12 @@ template <int RW>
 __device__ __forceinline__ int bfs_groups(const EnvDims &d) { return RW <= 3 ? (d.N + 1) >> 1 : d.N; }
 
 template <int RW>
-__device__ __noinline__ void bfs_group(const StepParams &p, const int e, const int grp)
+__device__ __forceinline__ void bfs_group_into(const StepParams &p, const int e, const int grp, uint32_t *navi)
 {
     const EnvDims &d = p.d;
     const int lane = threadIdx.x & 31;
     const uint32_t *obst = p.obst;
     const uint8_t *goal = p.goal;
-    int sel = 0;
-    if (lane == 0 && p.navi_alt) sel = __ldcg(p.navi_sel + e);
-    sel = __shfl_sync(MAPF_FULL_MASK, sel, 0);
-    uint32_t *navi = const_cast<uint32_t *>(sel ? p.navi_alt : p.navi);  // the slot's live buffer
     if constexpr (RW <= 3) {
         // 16 lanes x RPL rows hold the map: RPL = ceil(L / 16)
         const int a = 2 * grp + (lane >> 4);
@@ -198,11 +194,28 @@ __device__ __noinline__ void bfs_group(const StepParams &p, const int e, const i
     }
 }
 
+// the slot's live heuristic-map buffer
+__device__ __forceinline__ uint32_t *navi_live_of(const StepParams &p, const int e)
+{
+    int sel = 0;
+    if ((threadIdx.x & 31) == 0 && p.navi_alt) sel = __ldcg(p.navi_sel + e);
+    sel = __shfl_sync(MAPF_FULL_MASK, sel, 0);
+    return const_cast<uint32_t *>(sel ? p.navi_alt : p.navi);
+}
+
+// (out of line: the task path calls it from two places)
+template <int RW>
+__device__ __noinline__ void bfs_group(const StepParams &p, const int e, const int grp)
+{
+    bfs_group_into<RW>(p, e, grp, navi_live_of(p, e));
+}
+
 // ---- BFS task queue -------------------------------------------------------------------------------------------------
 // A re-generation is the generator (one warp, serial over the agents) followed by one BFS per agent group -- independent
 // searches, ~2/3 of the work.  The re-generating warp announces them in a ring entry {slot, next group, groups done}; every
 // warp looks at the open entries before it claims its next work item and takes a group with ONE fetch-and-add on the
-// entry's `next` word (no retry loops: thousands of warps arrive at once), so the searches of one slot run on many warps and
+// entry's `next` word (no retry loops: thousands of warps arrive at once; the owner takes four at a time, a helper two), so the
+// searches of one slot run on many warps and
 // a re-generation takes the generator's time plus about one search instead of all of them in sequence.
 // A free entry has next = kTqFree (negative as int32, far from wrapping): a claim succeeds iff 0 <= claimed < groups.  The
 // owner publishes slot BEFORE it zeroes next and frees the entry (next first) only after every group is done, so a
@@ -213,35 +226,37 @@ constexpr int kTqUnpublished = -2;         // tq_claim: reserved by an owner tha
 
 __device__ __forceinline__ uint32_t *tq_entry(const RolloutArgs &r, const uint32_t idx) { return r.tq + 4 + 4 * (idx % (uint32_t)r.tq_cap); }
 
-// claims one group of ring entry `ent`: >= 0 the group (and `e` the slot), -1 none left, kTqUnpublished
+// Claims up to `want` consecutive groups of ring entry `ent` with ONE fetch-and-add and runs them: returns how many it ran
+// (0: none left), or kTqUnpublished.  One fence + one add of the count publish the whole batch -- a claim / completion pair
+// costs three L2 round trips (~3 us), as much as half a search at 40x40.  `own`: the caller published the entry itself.
 template <int RW>
-__device__ __forceinline__ int tq_claim(const StepParams &p, uint32_t *ent, const int lane, int &e)
+__device__ __forceinline__ int tq_take(const StepParams &p, uint32_t *ent, const int lane, const int want, const bool own, const int own_e)
 {
-    int g = -1, slot = 0;
+    const int groups = bfs_groups<RW>(p.d);
+    int first = -1, slot = own_e;
     if (lane == 0) {
-        const int32_t c = (int32_t)atomicAdd(ent + 1, 1u);
-        if (c >= 0 && c < bfs_groups<RW>(p.d)) {
-            __threadfence();  // the claim before the slot (published before next was zeroed)
-            g = c;
-            slot = (int)ld_acquire_u32(ent);
+        const int32_t c = (int32_t)atomicAdd(ent + 1, (uint32_t)want);
+        if (c >= 0 && c < groups) {
+            first = c;
+            if (!own) {
+                __threadfence();  // the claim before the slot (published before next was zeroed)
+                slot = (int)ld_acquire_u32(ent);
+            }
         } else if (c < (int32_t)0xA0000000u) {
-            g = kTqUnpublished;
+            first = kTqUnpublished;
         }
     }
-    g = __shfl_sync(MAPF_FULL_MASK, g, 0);
-    e = __shfl_sync(MAPF_FULL_MASK, slot, 0);
-    return g;
-}
-
-template <int RW>
-__device__ __forceinline__ void tq_run(const StepParams &p, uint32_t *ent, const int e, const int g, const int lane)
-{
-    bfs_group<RW>(p, e, g);
+    first = __shfl_sync(MAPF_FULL_MASK, first, 0);
+    if (first < 0) return first == kTqUnpublished ? kTqUnpublished : 0;
+    const int e = __shfl_sync(MAPF_FULL_MASK, slot, 0);
+    const int last = min(first + want, groups);
+    for (int g = first; g < last; ++g) bfs_group<RW>(p, e, g);
     __syncwarp();
     if (lane == 0) {
         __threadfence();  // the tiles before the count
-        atomicAdd(ent + 2, 1u);
+        atomicAdd(ent + 2, (uint32_t)(last - first));
     }
+    return last - first;
 }
 
 // A warp between two work items lends a hand: it looks at ONE announced entry, picked pseudo-randomly among those past the
@@ -259,13 +274,8 @@ __device__ __forceinline__ void tq_help(const StepParams &p, const RolloutArgs &
     if (open <= 0) return;
     const uint32_t idx = h + (uint32_t)(((unsigned long long)(salt * 2654435761u) * (uint32_t)open) >> 32);
     uint32_t *ent = tq_entry(r, idx);
-    int e, g = -1;
-    for (int k = 0; k < 2; ++k) {
-        g = tq_claim<RW>(p, ent, lane, e);
-        if (g < 0) break;
-        tq_run<RW>(p, ent, e, g, lane);
-    }
-    if (g == -1 && idx == h && lane == 0) atomicMax(r.tq, h + 1);
+    const int took = tq_take<RW>(p, ent, lane, 2, false, 0);
+    if (took == 0 && idx == h && lane == 0) atomicMax(r.tq, h + 1);
 }
 
 // worker.py:422-428 inside the launch: a new instance for slot e (generator + heuristic maps of all its agents).  Instance
@@ -301,7 +311,8 @@ __device__ __noinline__ void regenerate_env(const StepParams &p, const RolloutAr
 #endif
     const int groups = bfs_groups<RW>(d);
     if (!r.tq) {
-        for (int grp = 0; grp < groups; ++grp) bfs_group<RW>(p, e, grp);
+        uint32_t *navi = navi_live_of(p, e);
+        for (int grp = 0; grp < groups; ++grp) bfs_group_into<RW>(p, e, grp, navi);
     } else {
         // announce the searches ...
         uint32_t idx = 0;
@@ -316,14 +327,16 @@ __device__ __noinline__ void regenerate_env(const StepParams &p, const RolloutAr
         }
         __syncwarp();
         // ... take part in them, and wait for the ones other warps took
-        int e2, g;
-        while ((g = tq_claim<RW>(p, ent, lane, e2)) >= 0) tq_run<RW>(p, ent, e2, g, lane);
+        while (tq_take<RW>(p, ent, lane, 4, true, e) > 0) {}
         unsigned spins = 0;
         for (;;) {
             uint32_t fin = 0;
             if (lane == 0) fin = ld_acquire_u32(ent + 2);
             fin = __shfl_sync(MAPF_FULL_MASK, fin, 0);
             if (fin == (uint32_t)groups) break;
+            // (work-conserving: when every warp is re-generating, a warp that only waited for the groups others took off its
+            // entry would leave the machine half idle)
+            tq_help<RW>(p, r, lane, (uint32_t)e * 31u + spins);
             __nanosleep(200);
             if (++spins > (1u << 22)) {  // a scheduling bug latches an error instead of hanging the GPU
                 if (lane == 0) atomicOr(p.err, MAPF_ERRBIT_INTERNAL);

@@ -50,6 +50,20 @@ int &rollout_pregen_ref()
     return v;
 }
 void mapf_set_rollout_pregen(int on) { rollout_pregen_ref() = on; }
+// MAPF_ROLLOUT_TASKS / mapf_debug_rollout_tasks: 1 = the searches of an in-launch re-generation are announced as tasks any warp
+// takes (mapf_rollout_device.cuh).  Off by default: it shortens a lone re-generation (the tail of a launch with FEW, LONG
+// re-generations: large maps, many agents, small batches) but a claim / completion pair costs ~3 us of L2 round trips per
+// batch of searches and a helper leaves the owner waiting -- at C2 / C3 (40x40) it is 0-3 % slower, and with every environment
+// re-generating at once 2.2x slower (profiles/r2_reset_cost.jsonl).
+int &rollout_tasks_ref()
+{
+    static int v = [] {
+        const char *s = std::getenv("MAPF_ROLLOUT_TASKS");
+        return s ? std::atoi(s) : 0;
+    }();
+    return v;
+}
+void mapf_set_rollout_tasks(int on) { rollout_tasks_ref() = on; }
 #ifdef MAPF_ENABLE_DIAG
 // diagnosis build only: per-item time stamps of the next rollout launches (profiles/tools/r2_rollout_timeline.py)
 static unsigned long long *g_trace = nullptr;
@@ -87,8 +101,7 @@ int mapf_launch_rollout(mapf_env *env, int e0, int e1, int T, const uint8_t *d_a
     r.tq = nullptr;
     int reserve_ctas = 0;
     if (r.max_steps > 0) {
-        static const int use_tq = [] { const char *v = std::getenv("MAPF_ROLLOUT_TASKS"); return v ? std::atoi(v) : 1; }();
-        if (use_tq) r.tq = env->ro_tq, r.tq_cap = env->ro_tq_cap;
+        if (rollout_tasks_ref()) r.tq = env->ro_tq, r.tq_cap = env->ro_tq_cap;
         // The environments that hit the cap inside this launch are known up front (rollout_prio_kernel), and their next
         // instances can be generated ahead by the dedicated generator / BFS kernels into the staging arrays and the second
         // heuristic-map buffer; the rollout kernel adopts them at the episode's end.

@@ -389,8 +389,8 @@ def test_rollout_full_size_c3_c4_vs_oracle(rollout_tuning, B, N, L, name):
 
 @pytest.mark.parametrize("B,N,L,cap,chunk,store", [(300, 1, 6, 9, 0, 0), (257, 2, 7, 6, 3, 1), (600, 8, 12, 5, 4, 0),
                                                      (96, 32, 40, 4, 2, 1), (40, 64, 40, 3, 5, 0), (24, 40, 64, 4, 0, 0)])
-@pytest.mark.parametrize("pregen", [2, 3, 0])
-def test_rollout_autoreset_vs_twin(rollout_tuning, B, N, L, cap, chunk, store, pregen):
+@pytest.mark.parametrize("pregen,tasks", [(2, 0), (3, 1), (0, 0), (0, 1)])
+def test_rollout_autoreset_vs_twin(rollout_tuning, B, N, L, cap, chunk, store, pregen, tasks):
     """Episode handling inside the launch (worker.py:390,422-428): a step that finds its environment finished -- all agents
     on their goals after the previous step (tiny boards reach that within a few random steps), or `cap` steps taken --
     re-generates the slot and emits the first observation.  The twin does the same through the public pieces:
@@ -405,6 +405,7 @@ def test_rollout_autoreset_vs_twin(rollout_tuning, B, N, L, cap, chunk, store, p
     seed, base, stride, density = 77, 1000, 4096, 0.2
     rollout_tuning(1, 0, chunk, store)
     _native.lib().mapf_debug_rollout_pregen(pregen)
+    _native.lib().mapf_debug_rollout_tasks(tasks)   # in-launch searches as tasks any warp takes / on the slot's own warp
     env, twin = make_env(B, N, L), make_env(B, N, L)
     for e in (env, twin):
         e.reset(seed=seed, env_offset=base, density=density)
@@ -422,6 +423,7 @@ def test_rollout_autoreset_vs_twin(rollout_tuning, B, N, L, cap, chunk, store, p
                  env.rollout(torch.roll(acts, shifts=-(T1 % A), dims=0), num_steps=T - T1, out_codes=codes[T1:])]
         obs, rew, done, steps = (torch.cat([a.clone(), b]) for a, b in zip(*parts))
     _native.lib().mapf_debug_rollout_pregen(1)
+    _native.lib().mapf_debug_rollout_tasks(0)
     episode = np.zeros(B, dtype=np.int64)
     fin = np.zeros(B, dtype=bool)
     n_resets = n_done = 0
