@@ -382,6 +382,34 @@ typedef struct mapf_replay_batch {
 int mapf_replay_gather(const mapf_replay_view *view, const int64_t *d_idx, int64_t batch, const mapf_replay_batch *out,
                        int32_t *d_err, void *stream);
 
+/* ---- CBS expert / solvable-instance generator (search.py:58-442, test.py:23-79) -- HOST code ------------------
+ * Conflict-based search over space-time A*: a collision-free set of paths of minimal sum of costs (search.py:17-21), as the
+ * action script search.find_path returns (search.py:396-442).  All pointers are HOST memory; no kernel is launched.
+ *   h_map     u8[L, L]   1 = obstacle                                  (CBSSolver(my_map, ...), search.py:277)
+ *   h_starts, h_goals u8[N, 2] (x, y)                                  (env.agents_pos / env.goals_pos, :400-402)
+ *   h_dist    i32[N, L, L] or NULL: per-agent distances to the goal, MAPF_DIST_UNREACHABLE where there is no path -- the
+ *             optional output of mapf_env_bfs_navi copied to the host (== search.compute_heuristics, :24-55); NULL computes
+ *             them here
+ *   max_steps            config.max_steps (256): low-level nodes at that timestep are not expanded (search.py:186-187)
+ *   time_limit_ms        wall-clock limit of the high-level search (the reference: 5000, search.py:320; 0 = none)
+ *   node_limit           high-level nodes expanded at most (>= 1; makes a bounded search reproducible)
+ *   h_actions_out u8[max_T, N] action ids of environment.py:12, one row per step, every path padded with stays
+ *   T_out     steps of the script (the reference's `opt_steps`, test.py:58); -1: no solution within the limits (find_path
+ *             returns None) or longer than max_T
+ *   cost_out  (optional) sum of costs; expanded_out (optional) high-level nodes expanded
+ * The sum of costs equals the reference's for every instance both solve (CBS is optimal whatever conflict it splits on); the
+ * paths are one of several optimal sets: the reference draws the conflict and the constrained agent with random.choice and
+ * stops on wall-clock time, here the search is deterministic (first conflict, standard split). */
+int mapf_cbs_solve(const uint8_t *h_map, int32_t map_length, int32_t num_agents, const uint8_t *h_starts, const uint8_t *h_goals,
+                   const int32_t *h_dist, int32_t max_steps, int32_t time_limit_ms, int64_t node_limit, uint8_t *h_actions_out,
+                   int32_t max_T, int32_t *T_out, int32_t *cost_out, int64_t *expanded_out);
+/* n instances of one geometry on `threads` host threads (0 = all): arrays as above with a leading dimension n
+ * (create_test's loop, test.py:47-58, with the solver calls in parallel). */
+int mapf_cbs_solve_batch(int32_t n, const uint8_t *h_maps, int32_t map_length, int32_t num_agents, const uint8_t *h_starts,
+                         const uint8_t *h_goals, const int32_t *h_dist, int32_t max_steps, int32_t time_limit_ms, int64_t node_limit,
+                         uint8_t *h_actions_out, int32_t max_T, int32_t *T_out, int32_t *cost_out, int64_t *expanded_out,
+                         int32_t threads);
+
 #ifdef __cplusplus
 }
 #endif

@@ -94,6 +94,8 @@ SIGNATURES = {
     "mapf_actor_td_n": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _f64, _vp, _vp]),
     "mapf_per_cycle": (C.c_int, [_vp, C.POINTER(PerCycleArgs), _vp]),
     "mapf_per_status": (C.c_int, [_vp, _vp]),
+    "mapf_cbs_solve": (C.c_int, [_vp, _i32, _i32, _vp, _vp, _vp, _i32, _i32, _i64, _vp, _i32, _vp, _vp, _vp]),
+    "mapf_cbs_solve_batch": (C.c_int, [_i32, _vp, _i32, _i32, _vp, _vp, _vp, _i32, _i32, _i64, _vp, _i32, _vp, _vp, _vp, _i32]),
 }
 
 
