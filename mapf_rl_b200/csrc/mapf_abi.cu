@@ -179,6 +179,11 @@ int mapf_env_create(const mapf_env_config *cfg, mapf_env **out)
     d.K = (d.N + 31) / 32;
     d.obst_stride = (d.R * d.RWS + 3) & ~3;
     d.navi_agent_stride = d.NB * d.NB * 32;
+    {
+        // MAPF_BFS_APW4=0: two agents per warp at every size (A/B runs)
+        static const int apw4 = [] { const char *v = std::getenv("MAPF_BFS_APW4"); return v ? std::atoi(v) : 1; }();
+        d.bfs_apw = (apw4 && d.RW == 2 && d.L <= 40) ? 4 : (d.RW <= 3 ? 2 : 1);
+    }
     env->device = cfg->device;
     env->num_sms = 148;
     cudaDeviceGetAttribute(&env->num_sms, cudaDevAttrMultiProcessorCount, cfg->device);

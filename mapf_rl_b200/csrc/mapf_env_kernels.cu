@@ -278,8 +278,9 @@ static int launch_bfs_rw(mapf_env *env, const int32_t *ids, const uint8_t *mask,
 {
     const bool pregen = pregen_min >= 0;
     const EnvDims &d = env->d;
-    // two agents per warp (16 lanes x RPL rows each) while an agent's rows fit 18 words per lane: every map of up to 88 cells a side
-    const int apw = RW <= 3 ? 2 : 1;
+    // four agents per warp (8 lanes x up to 5 rows each) for two-word maps of up to 40 cells a side, two (16 lanes x up to 6 rows)
+    // for every other map of up to 88 cells, else one
+    const int apw = d.bfs_apw;
     const int rpl = (d.L + 32 / apw - 1) / (32 / apw);
     const long warps = ((long)n * d.N + apw - 1) / apw;
     const int grid = pregen ? env->num_sms * 8 : (int)((warps + kBfsWarps - 1) / kBfsWarps);
@@ -301,11 +302,16 @@ static int launch_bfs_rw(mapf_env *env, const int32_t *ids, const uint8_t *mask,
             default: ok = false;
         }
     } else if constexpr (RW == 2) {
-        switch (rpl) {
-            case 2: MAPF_BFS_LAUNCH(2, 2); break;
-            case 3: MAPF_BFS_LAUNCH(3, 2); break;
-            case 4: MAPF_BFS_LAUNCH(4, 2); break;
-            default: ok = false;
+        if (apw == 4) {
+            if (rpl <= 4) MAPF_BFS_LAUNCH(4, 4);
+            else MAPF_BFS_LAUNCH(5, 4);
+        } else {
+            switch (rpl) {
+                case 2: MAPF_BFS_LAUNCH(2, 2); break;
+                case 3: MAPF_BFS_LAUNCH(3, 2); break;
+                case 4: MAPF_BFS_LAUNCH(4, 2); break;
+                default: ok = false;
+            }
         }
     } else if constexpr (RW == 3) {
         switch (rpl) {

@@ -159,8 +159,14 @@ __device__ __forceinline__ void load_env_state(const StepParams &p, const int e,
 
 // The heuristic maps of agent group `grp` of slot e (two agents, one per half warp, for maps of up to 88 cells a side, else
 // one) into the slot's live buffer: get_navi_map (environment.py:195) with the warp-level BFS of the load / reset path.
+// Agents per search pass inside the rollout kernel: two (16 lanes x up to 6 rows each) for maps of up to 88 cells a side, else
+// one.  (The load / reset kernels take FOUR agents per warp at 40x40 -- 8 % faster there; compiled into re-generation here, its
+// 40 live words per lane made the whole out-of-line function spill, generator included: 27 -> 31 us per step at C2.)
 template <int RW>
-__device__ __forceinline__ int bfs_groups(const EnvDims &d) { return RW <= 3 ? (d.N + 1) >> 1 : d.N; }
+__device__ __forceinline__ int bfs_groups(const EnvDims &d)
+{
+    return RW <= 3 ? (d.N + 1) >> 1 : d.N;
+}
 
 template <int RW>
 __device__ __forceinline__ void bfs_group_into(const StepParams &p, const int e, const int grp, uint32_t *navi)
@@ -278,6 +284,13 @@ __device__ __forceinline__ void tq_help(const StepParams &p, const RolloutArgs &
     if (took == 0 && idx == h && lane == 0) atomicMax(r.tq, h + 1);
 }
 
+// (out of line: one call in the work-item loop instead of the search's code and registers)
+template <int RW>
+__device__ __noinline__ void tq_help_call(const StepParams &p, const RolloutArgs &r, const uint32_t salt)
+{
+    tq_help<RW>(p, r, (int)(threadIdx.x & 31), salt);
+}
+
 // worker.py:422-428 inside the launch: a new instance for slot e (generator + heuristic maps of all its agents).  Instance
 // number n of slot e is global instance env_offset + n * stride + e of the Philox stream, i.e. what
 // mapf_env_reset(mask = {e}, seed, env_offset + n * stride) draws.  Kept out of line: it runs once per episode.
@@ -389,7 +402,10 @@ __device__ __forceinline__ void adopt_pregenerated(const StepParams &p, const Ro
     __syncwarp();
 }
 
-template <int RW, int K, int WARPS, int MINB>
+// EP: episode handling is compiled in.  The plain instantiation (r.max_steps == 0 launches) carries none of it -- the
+// re-generation / adoption / task code costs the stepping loop registers (128 per thread are all it has: spills) and
+// instruction-cache space even when it never runs: 21.5 -> 25.5 us per step at C2 when it was one kernel.
+template <int RW, int K, int WARPS, int MINB, bool EP>
 __global__ void __launch_bounds__(WARPS * 32, MINB)
 rollout_kernel(const __grid_constant__ StepParams p0, const __grid_constant__ RolloutArgs r)
 {
@@ -424,7 +440,7 @@ rollout_kernel(const __grid_constant__ StepParams p0, const __grid_constant__ Ro
     // priority items (see rollout_prio_kernel): used while they are a minority -- when most environments re-generate
     // inside the launch (T of the order of the cap or more) plain time-major chunks balance better
     unsigned nprio = 0;
-    if (r.prio) {
+    if (EP && r.prio) {
         nprio = __ldcg(r.prio);
         // (pre-generated instances are adopted, not generated here: no long items to hand out first)
         if (nprio * 4u > (unsigned)nenv || (r.pg_epi && !r.prio_last && nprio >= (unsigned)r.pregen_min)) nprio = 0;
@@ -433,7 +449,8 @@ rollout_kernel(const __grid_constant__ StepParams p0, const __grid_constant__ Ro
     bool bulk_used = false;
     uint32_t visits = 0;
     for (;;) {
-        if (r.tq) tq_help<RW>(p0, r, lane, (uint32_t)(blockIdx.x * WARPS + warp) + 7919u * ++visits);
+        if constexpr (EP)
+            if (r.tq) tq_help_call<RW>(p0, r, (uint32_t)(blockIdx.x * WARPS + warp) + 7919u * (uint32_t)visits++);
         unsigned long long it = 0;
         if (lane == 0) it = atomicAdd(r.work, 1ull);
         it = __shfl_sync(MAPF_FULL_MASK, it, 0);
@@ -495,7 +512,7 @@ rollout_kernel(const __grid_constant__ StepParams p0, const __grid_constant__ Ro
             uint8_t *obs_env = r.obs + ((size_t)so * d.B + e) * env_bytes;
             const int head = (int)(reinterpret_cast<uintptr_t>(obs_env) & 15);
             bool reset_step = false;
-            if (r.max_steps > 0) {
+            if (EP && r.max_steps > 0) {
                 // worker.py:390: the episode ended with the previous step (done, or the step cap) -> this step re-generates the
                 // slot and emits the new episode's first observation
                 const int st = __shfl_sync(MAPF_FULL_MASK, regs.step, 0);
@@ -595,7 +612,7 @@ rollout_kernel(const __grid_constant__ StepParams p0, const __grid_constant__ Ro
         if (left == (unsigned long long)gridDim.x * WARPS) {
             r.work[0] = 0ull;
             r.work[1] = 0ull;
-            if (r.tq) r.tq[0] = r.tq[1] = 0u;
+            if (EP && r.tq) r.tq[0] = r.tq[1] = 0u;
             __threadfence();
         }
     }
@@ -610,11 +627,11 @@ struct RolloutTuning {
 };
 
 // MINB = resident CTAs (of 2 warps) per SM the kernel is compiled for: 8 -> 128 registers per thread, 12 -> 85, 16 -> 64
-template <int RW, int K, int MINB>
+template <int RW, int K, int MINB, bool EP>
 int launch_rollout_cfg(mapf_env *env, const StepParams &p, RolloutArgs r, const RolloutTuning &tn, cudaStream_t st)
 {
     constexpr int WARPS = 2;
-    auto kern = rollout_kernel<RW, K, WARPS, MINB>;
+    auto kern = rollout_kernel<RW, K, WARPS, MINB, EP>;
     const EnvDims &d = env->d;
     // per-warp shared memory: step buffers | tile slots (16-byte aligned) | staging block of the bulk form
     const int step_words = (p.warp_smem_words + 3) & ~3;
@@ -626,7 +643,7 @@ int launch_rollout_cfg(mapf_env *env, const StepParams &p, RolloutArgs r, const 
     const size_t smem = (size_t)r.warp_words * 4 * WARPS;
     if (smem > 227 * 1024) return MAPF_EINVAL;  // the caller falls back to chains of single-step launches
     // resident CTAs per SM: cached per (kernel, shared-memory size)
-    const int key = ((RW * 8 + K) * 2 + r.store_mode) * 32 + MINB;
+    const int key = (((RW * 8 + K) * 2 + r.store_mode) * 32 + MINB) * 2 + (EP ? 1 : 0);
     if (env->ro_key != key) {
         int per_sm = 0;
         // the opt-in maximum, the same for every handle (a smaller value set later would break a larger handle's launches)
@@ -672,14 +689,14 @@ template <int MINB>
 int launch_rollout_class(mapf_env *env, const StepParams &p, const RolloutArgs &r, const RolloutTuning &tn, cudaStream_t st)
 {
     switch (env->d.RW * 10 + env->d.K) {
-        case 11: return launch_rollout_cfg<1, 1, MINB>(env, p, r, tn, st);
-        case 12: return launch_rollout_cfg<1, 2, MINB>(env, p, r, tn, st);
-        case 21: return launch_rollout_cfg<2, 1, MINB>(env, p, r, tn, st);
-        case 22: return launch_rollout_cfg<2, 2, MINB>(env, p, r, tn, st);
-        case 31: return launch_rollout_cfg<3, 1, MINB>(env, p, r, tn, st);
-        case 32: return launch_rollout_cfg<3, 2, MINB>(env, p, r, tn, st);
-        case 41: return launch_rollout_cfg<4, 1, MINB>(env, p, r, tn, st);
-        case 42: return launch_rollout_cfg<4, 2, MINB>(env, p, r, tn, st);
+        case 11: return r.max_steps > 0 ? launch_rollout_cfg<1, 1, MINB, true>(env, p, r, tn, st) : launch_rollout_cfg<1, 1, MINB, false>(env, p, r, tn, st);
+        case 12: return r.max_steps > 0 ? launch_rollout_cfg<1, 2, MINB, true>(env, p, r, tn, st) : launch_rollout_cfg<1, 2, MINB, false>(env, p, r, tn, st);
+        case 21: return r.max_steps > 0 ? launch_rollout_cfg<2, 1, MINB, true>(env, p, r, tn, st) : launch_rollout_cfg<2, 1, MINB, false>(env, p, r, tn, st);
+        case 22: return r.max_steps > 0 ? launch_rollout_cfg<2, 2, MINB, true>(env, p, r, tn, st) : launch_rollout_cfg<2, 2, MINB, false>(env, p, r, tn, st);
+        case 31: return r.max_steps > 0 ? launch_rollout_cfg<3, 1, MINB, true>(env, p, r, tn, st) : launch_rollout_cfg<3, 1, MINB, false>(env, p, r, tn, st);
+        case 32: return r.max_steps > 0 ? launch_rollout_cfg<3, 2, MINB, true>(env, p, r, tn, st) : launch_rollout_cfg<3, 2, MINB, false>(env, p, r, tn, st);
+        case 41: return r.max_steps > 0 ? launch_rollout_cfg<4, 1, MINB, true>(env, p, r, tn, st) : launch_rollout_cfg<4, 1, MINB, false>(env, p, r, tn, st);
+        case 42: return r.max_steps > 0 ? launch_rollout_cfg<4, 2, MINB, true>(env, p, r, tn, st) : launch_rollout_cfg<4, 2, MINB, false>(env, p, r, tn, st);
     }
     return MAPF_EINVAL;
 }
