@@ -163,7 +163,11 @@ __device__ __forceinline__ void reset_env_warp(const EnvDims &d, const int e, co
     }
     const uint32_t thresh = dens <= 0.f ? 0u : (dens >= 1.f ? 0xffffffffu : (uint32_t)((double)dens * 4294967296.0));
 
-    Bits<RW, RPL> fre, elig, comp;
+    // `comp` caches the component of the last start cell, `big` the largest component filled so far: almost every start falls
+    // into the giant component, but every start that does not used to evict it from the (single) cache and the next agent
+    // paid for another ~70-iteration flood fill of the giant component -- half of the generator's instructions at density 0.3
+    Bits<RW, RPL> fre, elig, comp, big;
+    int big_n = 0;
     for (uint32_t attempt = 0;; ++attempt) {
         if (attempt >= 256) {  // practically unreachable: e.g. density ~1 or more agents than usable cells
             if (lane == 0) atomicOr(err, MAPF_ERRBIT_RESET);
@@ -199,7 +203,9 @@ __device__ __forceinline__ void reset_env_warp(const EnvDims &d, const int e, co
             for (int w = 0; w < RW; ++w) {
                 elig.v[q][w] &= fre.v[q][w];
                 comp.v[q][w] = 0;
+                big.v[q][w] = 0;
             }
+        big_n = 0;
         // ---- agents ----
         bool ok = true;
         for (int i = 0; i < N; ++i) {
@@ -210,7 +216,12 @@ __device__ __forceinline__ void reset_env_warp(const EnvDims &d, const int e, co
                 ok = false;
                 break;
             }
-            if (!test_cell(comp, s, lane)) {
+            if (!test_cell(comp, s, lane) && big_n > 0 && test_cell(big, s, lane)) {
+#pragma unroll
+                for (int q = 0; q < RPL; ++q)
+#pragma unroll
+                    for (int w = 0; w < RW; ++w) comp.v[q][w] = big.v[q][w];
+            } else if (!test_cell(comp, s, lane)) {
                 // flood fill the component of s over the full free map
 #pragma unroll
                 for (int q = 0; q < RPL; ++q)
@@ -237,6 +248,14 @@ __device__ __forceinline__ void reset_env_warp(const EnvDims &d, const int e, co
                             grew |= add;
                         }
                     if (!__any_sync(MAPF_FULL_MASK, grew != 0)) break;
+                }
+                const int n = __reduce_add_sync(MAPF_FULL_MASK, count_bits(comp));
+                if (n > big_n) {
+                    big_n = n;
+#pragma unroll
+                    for (int q = 0; q < RPL; ++q)
+#pragma unroll
+                        for (int w = 0; w < RW; ++w) big.v[q][w] = comp.v[q][w];
                 }
             }
             clear_cell(elig, s, lane);
