@@ -182,16 +182,13 @@ __device__ __forceinline__ void reset_env_warp(const EnvDims &d, const int e, co
             if (row < L) {
                 for (int y4 = 0; y4 < L; y4 += 4) {
                     const uint4 r = philox4x32_10(make_uint4(g_lo, g_hi, PURPOSE_MAP | (attempt << 8), (uint32_t)(row * 64 + (y4 >> 2))), key);
-                    const uint32_t rr[4] = {r.x, r.y, r.z, r.w};
+                    // the four cells as one nibble at padded column y4 + 4 (a multiple of 4: it never straddles two words)
+                    uint32_t nib = (r.x >= thresh ? 1u : 0u) | (r.y >= thresh ? 2u : 0u) | (r.z >= thresh ? 4u : 0u) | (r.w >= thresh ? 8u : 0u);
+                    if (y4 + 4 > L) nib &= (1u << (L - y4)) - 1u;
+                    const int p = y4 + 4;
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const int p = y4 + j + 4;  // padded column
-                        if (y4 + j < L && rr[j] >= thresh) {
-#pragma unroll
-                            for (int w = 0; w < RW; ++w)
-                                if ((p >> 5) == w) fre.v[q][w] |= 1u << (p & 31);
-                        }
-                    }
+                    for (int w = 0; w < RW; ++w)
+                        if ((p >> 5) == w) fre.v[q][w] |= nib << (p & 31);
                 }
             }
         }

@@ -147,3 +147,18 @@ def test_full_board_and_overfull_board():
     env.reset(seed=0, density=0.0)
     with pytest.raises(RuntimeError):
         env.check()
+
+
+@pytest.mark.gpu
+def test_generator_stream_is_pinned():
+    """The instances of (seed, env_offset) are part of the contract (sharding, replay of a run): optimisations of the generator /
+    BFS kernels must not move them.  Hash recorded with the build of round 2 (profiles/tools/r2_instance_hash.py)."""
+    import hashlib
+    h = hashlib.sha256()
+    for (B, N, L, dens) in ((512, 32, 40, 0.3), (128, 64, 80, 0.3), (256, 7, 13, None), (64, 100, 120, 0.2)):
+        env = make_env(B, N, L)
+        env.reset(seed=5, env_offset=17, density=dens)
+        env.check()
+        for t in (env.map, env.agents_pos, env.goals_pos):
+            h.update(t.cpu().numpy().tobytes())
+    assert h.hexdigest() == "626f27b297399fc2c8df0dd88a7e374ea8ede2e1fabd5adecfee589bf2d4b65e"
