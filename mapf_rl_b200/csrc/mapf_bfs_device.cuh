@@ -38,18 +38,39 @@ __device__ __forceinline__ uint32_t bfs_column_mask(int L, int w)
     return (hi - lo == 32) ? 0xffffffffu : (((1u << (hi - lo)) - 1u) << lo);
 }
 
+// free cells of this lane's map rows: the same for every agent of the environment (a caller that searches for one agent
+// after the other loads them once)
+template <int RW, int RPL>
+struct BfsFree {
+    uint32_t v[RPL][RW];
+};
+
 template <int RW, int RPL, int APW>
-__device__ __forceinline__ void bfs_init(const EnvDims &d, const uint32_t *ob, const int gx, const int gy, const bool alive,
-                                         BfsState<RW, RPL> &S)
+__device__ __forceinline__ void bfs_load_free(const EnvDims &d, const uint32_t *ob, BfsFree<RW, RPL> &F)
 {
     constexpr int LW = 32 / APW;
     const int lane = (threadIdx.x & 31) % LW;    // lane within the agent's group
 #pragma unroll
     for (int q = 0; q < RPL; ++q) {
-        const int row = alive ? lane * RPL + q : d.L;  // a group without an agent owns no rows
+        const int row = lane * RPL + q;
+#pragma unroll
+        for (int w = 0; w < RW; ++w)
+            F.v[q][w] = (row < d.L) ? (~__ldcg(ob + (row + 4) * d.RWS + w) & bfs_column_mask(d.L, w)) : 0u;
+    }
+}
+
+template <int RW, int RPL, int APW>
+__device__ __forceinline__ void bfs_init(const EnvDims &d, const BfsFree<RW, RPL> &F, const int gx, const int gy, const bool alive,
+                                         BfsState<RW, RPL> &S)
+{
+    constexpr int LW = 32 / APW;
+    const int lane = (threadIdx.x & 31) % LW;
+#pragma unroll
+    for (int q = 0; q < RPL; ++q) {
+        const int row = lane * RPL + q;
 #pragma unroll
         for (int w = 0; w < RW; ++w) {
-            const uint32_t fre = (row < d.L) ? (~__ldcg(ob + (row + 4) * d.RWS + w) & bfs_column_mask(d.L, w)) : 0u;
+            const uint32_t fre = alive ? F.v[q][w] : 0u;  // a group without an agent owns no rows
             const int p = gy + 4;
             S.fro[q][w] = (row == gx && (p >> 5) == w) ? ((1u << (p & 31)) & fre) : 0u;
             S.unv[q][w] = fre & ~S.fro[q][w];
@@ -117,9 +138,11 @@ __device__ __forceinline__ void bfs_apply(BfsState<RW, RPL> &S, const uint32_t (
 // cell c iff (c in m1, n in z) or (c in m2, n in m1) or (c in z, n in m2) -- emitted as the overlapping 16x16 tiles
 // (mapf_common.cuh): a map row is padded row pr = row + 4, which is row pr & 7 of tile row-block pr >> 3 and row
 // (pr & 7) + 8 of the block above.
-template <int RW, int RPL, int APW>
-__device__ __forceinline__ void bfs_emit(const EnvDims &d, const uint32_t *ob, const int e, const int a, const bool alive,
-                                         const BfsState<RW, RPL> &S, uint32_t *__restrict__ navi)
+// KEEP: the caller's free rows are still live (one agent after the other with the rows loaded once); else they are read
+// again here, which keeps them out of the wave loop's register budget (the 64-register load / reset kernels).
+template <int RW, int RPL, int APW, bool KEEP>
+__device__ __forceinline__ void bfs_emit(const EnvDims &d, const uint32_t *ob, const BfsFree<RW, RPL> &F, const int e, const int a,
+                                         const bool alive, const BfsState<RW, RPL> &S, uint32_t *__restrict__ navi)
 {
     constexpr int LW = 32 / APW;
     const int lane = (threadIdx.x & 31) % LW;
@@ -130,7 +153,9 @@ __device__ __forceinline__ void bfs_emit(const EnvDims &d, const uint32_t *ob, c
         const int row = alive ? lane * RPL + q : d.L;
 #pragma unroll
         for (int w = 0; w < RW; ++w) {
-            const uint32_t fre = (row < d.L) ? (~__ldcg(ob + (row + 4) * d.RWS + w) & bfs_column_mask(d.L, w)) : 0u;
+            uint32_t fre;
+            if constexpr (KEEP) fre = alive ? F.v[q][w] : 0u;
+            else fre = (row < d.L) ? (~__ldcg(ob + (row + 4) * d.RWS + w) & bfs_column_mask(d.L, w)) : 0u;
             z[q][w] = fre & ~S.unv[q][w] & ~S.m1[q][w] & ~S.m2[q][w];
         }
     }
@@ -191,18 +216,15 @@ __device__ __forceinline__ void bfs_emit(const EnvDims &d, const uint32_t *ob, c
 // only: a wave that finds nothing is followed by waves that find nothing, so at most two idle waves are run at the end.
 // DIST: int32 distances are emitted too (parity with search.compute_heuristics) -- a separate instantiation, so the common
 // loop carries none of it.
-template <int RW, int RPL, int APW, bool WRAP, bool DIST>
+template <int RW, int RPL, int APW, bool WRAP, bool DIST, bool KEEP>
 __device__ __forceinline__ void bfs_navi_search(const EnvDims &d, const int e, const int a, const int i, const bool alive,
-                                                const uint32_t *__restrict__ obst, const uint8_t *__restrict__ goal,
+                                                const uint32_t *__restrict__ ob, const BfsFree<RW, RPL> &F, const int gx, const int gy,
                                                 uint32_t *__restrict__ navi, int32_t *__restrict__ dist_out)
 {
     constexpr int LW = 32 / APW;
     const int lane = (threadIdx.x & 31) % LW;
-    const uint32_t *ob = obst + (size_t)e * d.obst_stride;
-    const uchar2 gg = __ldcg(reinterpret_cast<const uchar2 *>(goal) + (size_t)e * d.N + a);
-    const int gx = gg.x, gy = gg.y;
     BfsState<RW, RPL> S;
-    bfs_init<RW, RPL, APW>(d, ob, gx, gy, alive, S);
+    bfs_init<RW, RPL, APW>(d, F, gx, gy, alive, S);
 
     int32_t *dist = nullptr;
     if constexpr (DIST) {
@@ -246,7 +268,7 @@ __device__ __forceinline__ void bfs_navi_search(const EnvDims &d, const int e, c
         const uint32_t any = wave(std::integral_constant<int, 0>{}, t + 2);
         if (!__any_sync(MAPF_FULL_MASK, any != 0)) break;
     }
-    bfs_emit<RW, RPL, APW>(d, ob, e, a, alive, S, navi);
+    bfs_emit<RW, RPL, APW, KEEP>(d, ob, F, e, a, alive, S, navi);
 }
 
 // All 32 lanes call together; picks the instantiation (uniform branches: L and dist_out are launch-wide).
@@ -256,9 +278,24 @@ __device__ __forceinline__ void bfs_navi_warp(const EnvDims &d, const int e, con
                                               uint32_t *__restrict__ navi, int32_t *__restrict__ dist_out)
 {
     constexpr int LW = 32 / APW;
-    if (dist_out) bfs_navi_search<RW, RPL, APW, false, true>(d, e, a, i, alive, obst, goal, navi, dist_out);
-    else if (d.L < LW * RPL) bfs_navi_search<RW, RPL, APW, true, false>(d, e, a, i, alive, obst, goal, navi, nullptr);
-    else bfs_navi_search<RW, RPL, APW, false, false>(d, e, a, i, alive, obst, goal, navi, nullptr);
+    const uint32_t *ob = obst + (size_t)e * d.obst_stride;
+    const uchar2 gg = __ldcg(reinterpret_cast<const uchar2 *>(goal) + (size_t)e * d.N + a);
+    BfsFree<RW, RPL> F;
+    bfs_load_free<RW, RPL, APW>(d, ob, F);
+    if (dist_out) bfs_navi_search<RW, RPL, APW, false, true, false>(d, e, a, i, alive, ob, F, gg.x, gg.y, navi, dist_out);
+    else if (d.L < LW * RPL) bfs_navi_search<RW, RPL, APW, true, false, false>(d, e, a, i, alive, ob, F, gg.x, gg.y, navi, nullptr);
+    else bfs_navi_search<RW, RPL, APW, false, false, false>(d, e, a, i, alive, ob, F, gg.x, gg.y, navi, nullptr);
+}
+
+// The same for a caller that searches for the agents of ONE environment one group after the other (in-launch re-generation):
+// the free rows and the goal arrive in registers, loaded once per environment instead of once (twice: emit) per group.
+template <int RW, int RPL, int APW>
+__device__ __forceinline__ void bfs_navi_warp_pre(const EnvDims &d, const int e, const int a, const bool alive, const uint32_t *__restrict__ ob,
+                                                  const BfsFree<RW, RPL> &F, const int gx, const int gy, uint32_t *__restrict__ navi)
+{
+    constexpr int LW = 32 / APW;
+    if (d.L < LW * RPL) bfs_navi_search<RW, RPL, APW, true, false, true>(d, e, a, 0, alive, ob, F, gx, gy, navi, nullptr);
+    else bfs_navi_search<RW, RPL, APW, false, false, true>(d, e, a, 0, alive, ob, F, gx, gy, navi, nullptr);
 }
 
 }  // namespace

@@ -200,6 +200,57 @@ __device__ __forceinline__ void bfs_group_into(const StepParams &p, const int e,
     }
 }
 
+// Every agent group of slot e, one after the other on this warp: the free rows of the map and the goals are loaded ONCE (a
+// search used to start with two dependent L2 round trips -- goal, then rows -- and to read the rows again when it emitted its
+// tiles: ~2 us of a ~10-us search).
+template <int RW>
+__device__ __forceinline__ void bfs_all_groups(const StepParams &p, const int e, uint32_t *navi)
+{
+    const EnvDims &d = p.d;
+    const int lane = threadIdx.x & 31;
+    const uint32_t *ob = p.obst + (size_t)e * d.obst_stride;
+    // goals of agents lane and lane + 32 (the rollout kernel serves up to 64 agents)
+    uchar2 g0 = make_uchar2(0, 0), g1 = make_uchar2(0, 0);
+    if (lane < d.N) g0 = __ldcg(reinterpret_cast<const uchar2 *>(p.goal) + (size_t)e * d.N + lane);
+    if (lane + 32 < d.N) g1 = __ldcg(reinterpret_cast<const uchar2 *>(p.goal) + (size_t)e * d.N + lane + 32);
+    const int gp0 = g0.x | (g0.y << 8), gp1 = g1.x | (g1.y << 8);
+    if constexpr (RW <= 3) {
+        auto all = [&](auto rplc) {
+            constexpr int RPL = decltype(rplc)::value;
+            BfsFree<RW, RPL> F;
+            bfs_load_free<RW, RPL, 2>(d, ob, F);
+            for (int grp = 0; 2 * grp < d.N; ++grp) {
+                const int a = 2 * grp + (lane >> 4);
+                const bool alive = a < d.N;
+                const int v0 = __shfl_sync(MAPF_FULL_MASK, gp0, a & 31), v1 = __shfl_sync(MAPF_FULL_MASK, gp1, a & 31);
+                const int gp = a < 32 ? v0 : v1;
+                bfs_navi_warp_pre<RW, RPL, 2>(d, e, alive ? a : 0, alive, ob, F, gp & 0xff, gp >> 8, navi);
+            }
+        };
+        const int rpl = (d.L + 15) >> 4;
+        if constexpr (RW == 1) {
+            if (rpl <= 1) all(std::integral_constant<int, 1>{});
+            else all(std::integral_constant<int, 2>{});
+        } else if constexpr (RW == 2) {
+            if (rpl <= 2) all(std::integral_constant<int, 2>{});
+            else if (rpl == 3) all(std::integral_constant<int, 3>{});
+            else all(std::integral_constant<int, 4>{});
+        } else {
+            if (rpl <= 4) all(std::integral_constant<int, 4>{});
+            else if (rpl == 5) all(std::integral_constant<int, 5>{});
+            else all(std::integral_constant<int, 6>{});
+        }
+    } else {
+        BfsFree<RW, 4> F;
+        bfs_load_free<RW, 4, 1>(d, ob, F);
+        for (int a = 0; a < d.N; ++a) {
+            const int v0 = __shfl_sync(MAPF_FULL_MASK, gp0, a & 31), v1 = __shfl_sync(MAPF_FULL_MASK, gp1, a & 31);
+            const int gp = a < 32 ? v0 : v1;
+            bfs_navi_warp_pre<RW, 4, 1>(d, e, a, true, ob, F, gp & 0xff, gp >> 8, navi);
+        }
+    }
+}
+
 // the slot's live heuristic-map buffer
 __device__ __forceinline__ uint32_t *navi_live_of(const StepParams &p, const int e)
 {
@@ -324,8 +375,7 @@ __device__ __noinline__ void regenerate_env(const StepParams &p, const RolloutAr
 #endif
     const int groups = bfs_groups<RW>(d);
     if (!r.tq) {
-        uint32_t *navi = navi_live_of(p, e);
-        for (int grp = 0; grp < groups; ++grp) bfs_group_into<RW>(p, e, grp, navi);
+        bfs_all_groups<RW>(p, e, navi_live_of(p, e));
     } else {
         // announce the searches ...
         uint32_t idx = 0;
