@@ -21,6 +21,12 @@
 
 namespace {
 
+#ifdef MAPF_ENABLE_DIAG
+// diagnosis build: cycles of a search's phases, summed over the searches of environment 0 ([0] init, [1] waves, [2] emit,
+// [3] searches, [4] wave triples); one atomic per search
+__device__ unsigned long long g_bfs_cycles[8];
+#endif
+
 // state of one agent's search in its lanes' registers
 template <int RW, int RPL>
 struct BfsState {
@@ -223,8 +229,15 @@ __device__ __forceinline__ void bfs_navi_search(const EnvDims &d, const int e, c
 {
     constexpr int LW = 32 / APW;
     const int lane = (threadIdx.x & 31) % LW;
+#ifdef MAPF_ENABLE_DIAG
+    const long long tb0 = clock64();
+    long long triples = 0;
+#endif
     BfsState<RW, RPL> S;
     bfs_init<RW, RPL, APW>(d, F, gx, gy, alive, S);
+#ifdef MAPF_ENABLE_DIAG
+    const long long tb1 = clock64();
+#endif
 
     int32_t *dist = nullptr;
     if constexpr (DIST) {
@@ -266,9 +279,25 @@ __device__ __forceinline__ void bfs_navi_search(const EnvDims &d, const int e, c
         wave(std::integral_constant<int, 1>{}, t);
         wave(std::integral_constant<int, 2>{}, t + 1);
         const uint32_t any = wave(std::integral_constant<int, 0>{}, t + 2);
+#ifdef MAPF_ENABLE_DIAG
+        ++triples;
+#endif
         if (!__any_sync(MAPF_FULL_MASK, any != 0)) break;
     }
+#ifdef MAPF_ENABLE_DIAG
+    const long long tb2 = clock64();
+#endif
     bfs_emit<RW, RPL, APW, KEEP>(d, ob, F, e, a, alive, S, navi);
+#ifdef MAPF_ENABLE_DIAG
+    if (e == 0 && (threadIdx.x & 31) == 0) {
+        const long long tb3 = clock64();
+        atomicAdd(&g_bfs_cycles[0], (unsigned long long)(tb1 - tb0));
+        atomicAdd(&g_bfs_cycles[1], (unsigned long long)(tb2 - tb1));
+        atomicAdd(&g_bfs_cycles[2], (unsigned long long)(tb3 - tb2));
+        atomicAdd(&g_bfs_cycles[3], 1ull);
+        atomicAdd(&g_bfs_cycles[4], (unsigned long long)triples);
+    }
+#endif
 }
 
 // All 32 lanes call together; picks the instantiation (uniform branches: L and dist_out are launch-wide).

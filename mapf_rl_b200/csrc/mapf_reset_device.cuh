@@ -40,6 +40,20 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k)
 
 enum : uint32_t { PURPOSE_DENSITY = 0, PURPOSE_MAP = 1, PURPOSE_AGENT = 2 };
 
+#ifdef MAPF_ENABLE_DIAG
+// diagnosis build: cycles of the generator's phases for environment 0 (profiles/tools/r2_generator_phases.py); accumulated in
+// registers and written once at the end (a global read-modify-write per tick would be what gets measured)
+__device__ unsigned long long g_reset_cycles[8];
+#define MAPF_RESET_TICK(slot)                 \
+    do {                                      \
+        const long long _now = clock64();     \
+        _acc[slot] += _now - _t0;             \
+        _t0 = _now;                           \
+    } while (0)
+#else
+#define MAPF_RESET_TICK(slot) do {} while (0)
+#endif
+
 template <int RW, int RPL>
 struct Bits {
     uint32_t v[RPL][RW];
@@ -79,27 +93,48 @@ __device__ __forceinline__ int count_bits(const Bits<RW, RPL> &m)
     return c;
 }
 
+// position of the n-th (0-based) set bit of m (n < popc(m)): five halving steps (__fns is a ~100-instruction sequence)
+__device__ __forceinline__ int nth_set_bit(uint32_t m, int n)
+{
+    int pos = 0;
+#pragma unroll
+    for (int half = 16; half >= 1; half >>= 1) {
+        const int c = __popc(m & ((1u << half) - 1u));
+        if (n >= c) {
+            n -= c;
+            pos += half;
+            m >>= half;
+        }
+    }
+    return pos;
+}
+
 // Uniform pick among the set bits of a warp-wide bitmap: returns (row << 8) | padded column, or -1 if the
-// bitmap is empty.  `total_out` receives the number of set bits.
+// bitmap is empty.  `total_out` receives the number of set bits.  The pick is the r-th set bit in (lane, q, w, bit) order,
+// r = floor(rnd * total / 2^32).  Written for LATENCY -- an in-launch re-generation runs two picks per agent on one warp, and
+// they were two thirds of the generator's 54 us (profiles/r2_generator_phases.jsonl): the exclusive prefix of the per-lane
+// counts comes from bit-sliced ballots (independent votes instead of a five-step shuffle scan), the bit inside the owning
+// word from nth_set_bit, and the owner's answer reaches the warp through one OR-reduction.
 template <int RW, int RPL>
 __device__ __forceinline__ int pick_bit(const Bits<RW, RPL> &m, uint32_t rnd, int lane, int &total_out)
 {
+    constexpr int kMax = 32 * RW * RPL;                                    // a lane's count is at most this
+    constexpr int kBits = kMax >= 512 ? 10 : (kMax >= 256 ? 9 : (kMax >= 128 ? 8 : (kMax >= 64 ? 7 : 6)));
     const int c = count_bits(m);
-    int incl = c;
+    const uint32_t lt = (1u << lane) - 1u;
+    int excl = 0, total = 0;
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const int t = __shfl_up_sync(MAPF_FULL_MASK, incl, o);
-        if (lane >= o) incl += t;
+    for (int k = 0; k < kBits; ++k) {
+        const uint32_t b = __ballot_sync(MAPF_FULL_MASK, (c >> k) & 1);
+        excl += __popc(b & lt) << k;
+        total += __popc(b) << k;
     }
-    const int total = __shfl_sync(MAPF_FULL_MASK, incl, 31);
     total_out = total;
     if (total == 0) return -1;
     const int r = (int)__umulhi(rnd, (uint32_t)total);
-    const int excl = incl - c;
-    const bool mine = r >= excl && r < incl;
-    int code = 0;
-    if (mine) {
-        int local = r - excl;
+    int local = r - excl;
+    uint32_t code = 0;
+    if (local >= 0 && local < c) {
         bool found = false;
 #pragma unroll
         for (int q = 0; q < RPL; ++q)
@@ -107,15 +142,13 @@ __device__ __forceinline__ int pick_bit(const Bits<RW, RPL> &m, uint32_t rnd, in
             for (int w = 0; w < RW; ++w) {
                 const int pc = __popc(m.v[q][w]);
                 if (!found && local < pc) {
-                    const int bit = __fns(m.v[q][w], 0, local + 1);
-                    code = ((lane + 32 * q) << 8) | (32 * w + bit);
+                    code = (uint32_t)((((lane + 32 * q) << 8) | (32 * w + nth_set_bit(m.v[q][w], local))) + 1);
                     found = true;
                 }
                 if (!found) local -= pc;
             }
     }
-    const int owner = __ffs(__ballot_sync(MAPF_FULL_MASK, mine)) - 1;
-    return __shfl_sync(MAPF_FULL_MASK, code, owner);
+    return (int)__reduce_or_sync(MAPF_FULL_MASK, code) - 1;  // exactly one lane owns the r-th bit
 }
 
 template <int RW, int RPL>
@@ -168,6 +201,10 @@ __device__ __forceinline__ void reset_env_warp(const EnvDims &d, const int e, co
     // paid for another ~70-iteration flood fill of the giant component -- half of the generator's instructions at density 0.3
     Bits<RW, RPL> fre, elig, comp, big;
     int big_n = 0;
+#ifdef MAPF_ENABLE_DIAG
+    long long _t0 = clock64();
+    long long _acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#endif
     for (uint32_t attempt = 0;; ++attempt) {
         if (attempt >= 256) {  // practically unreachable: e.g. density ~1 or more agents than usable cells
             if (lane == 0) atomicOr(err, MAPF_ERRBIT_RESET);
@@ -192,6 +229,7 @@ __device__ __forceinline__ void reset_env_warp(const EnvDims &d, const int e, co
                 }
             }
         }
+        MAPF_RESET_TICK(0);  // map
         // ---- cells of components with >= 2 cells: free with a free neighbour ----
         dilate(fre, elig, lane);
 #pragma unroll
@@ -205,10 +243,27 @@ __device__ __forceinline__ void reset_env_warp(const EnvDims &d, const int e, co
         big_n = 0;
         // ---- agents ----
         bool ok = true;
+        MAPF_RESET_TICK(1);  // eligibility
+        // the agents' draws, all at once: lane l holds those of agents l, l + 32, ... (the loop below is one dependent chain per
+        // agent; ten Philox rounds at its head were 200 cycles of it)
+        uint32_t draw_x[MAPF_MAX_AGENTS / 32], draw_y[MAPF_MAX_AGENTS / 32];
+#pragma unroll
+        for (int k = 0; k < MAPF_MAX_AGENTS / 32; ++k) {
+            draw_x[k] = draw_y[k] = 0;
+            if (k * 32 < N) {
+                const uint4 r = philox4x32_10(make_uint4(g_lo, g_hi, PURPOSE_AGENT | (attempt << 8), (uint32_t)(k * 32 + lane)), key);
+                draw_x[k] = r.x, draw_y[k] = r.y;
+            }
+        }
         for (int i = 0; i < N; ++i) {
-            const uint4 r = philox4x32_10(make_uint4(g_lo, g_hi, PURPOSE_AGENT | (attempt << 8), (uint32_t)i), key);
+            uint2 r = make_uint2(0u, 0u);
+#pragma unroll
+            for (int k = 0; k < MAPF_MAX_AGENTS / 32; ++k)
+                if ((i >> 5) == k) r = make_uint2(__shfl_sync(MAPF_FULL_MASK, draw_x[k], i & 31), __shfl_sync(MAPF_FULL_MASK, draw_y[k], i & 31));
+            MAPF_RESET_TICK(2);  // agent draw
             int total;
             const int s = pick_bit(elig, r.x, lane, total);
+            MAPF_RESET_TICK(3);  // first pick
             if (s < 0) {  // the reference regenerates the map (:107-110) / would raise mid-way; we redraw
                 ok = false;
                 break;
@@ -233,17 +288,22 @@ __device__ __forceinline__ void reset_env_warp(const EnvDims &d, const int e, co
                             if (lane + 32 * q == row && (col >> 5) == w) comp.v[q][w] = 1u << (col & 31);
                 }
                 for (;;) {
-                    Bits<RW, RPL> nb;
-                    dilate(comp, nb, lane);
+                    // four dilations per vote (a converged fill is a fixed point: the extra ones change nothing)
                     uint32_t grew = 0;
 #pragma unroll
-                    for (int q = 0; q < RPL; ++q)
+                    for (int rep = 0; rep < 4; ++rep) {
+                        Bits<RW, RPL> nb;
+                        dilate(comp, nb, lane);
+                        grew = 0;
 #pragma unroll
-                        for (int w = 0; w < RW; ++w) {
-                            const uint32_t add = nb.v[q][w] & fre.v[q][w] & ~comp.v[q][w];
-                            comp.v[q][w] |= add;
-                            grew |= add;
-                        }
+                        for (int q = 0; q < RPL; ++q)
+#pragma unroll
+                            for (int w = 0; w < RW; ++w) {
+                                const uint32_t add = nb.v[q][w] & fre.v[q][w] & ~comp.v[q][w];
+                                comp.v[q][w] |= add;
+                                grew |= add;
+                            }
+                    }
                     if (!__any_sync(MAPF_FULL_MASK, grew != 0)) break;
                 }
                 const int n = __reduce_add_sync(MAPF_FULL_MASK, count_bits(comp));
@@ -255,6 +315,7 @@ __device__ __forceinline__ void reset_env_warp(const EnvDims &d, const int e, co
                         for (int w = 0; w < RW; ++w) big.v[q][w] = comp.v[q][w];
                 }
             }
+            MAPF_RESET_TICK(4);  // component (cache test / flood fill)
             clear_cell(elig, s, lane);
             Bits<RW, RPL> cand;
 #pragma unroll
@@ -270,6 +331,7 @@ __device__ __forceinline__ void reset_env_warp(const EnvDims &d, const int e, co
 #pragma unroll
                     for (int w = 0; w < RW; ++w) elig.v[q][w] &= ~comp.v[q][w];
             }
+            MAPF_RESET_TICK(5);  // second pick + bookkeeping
             if (lane == 0) {
                 const size_t o = ((size_t)e * N + i) * 2;
                 pos[o] = (uint8_t)(s >> 8);
@@ -277,6 +339,7 @@ __device__ __forceinline__ void reset_env_warp(const EnvDims &d, const int e, co
                 goal[o] = (uint8_t)(t >> 8);
                 goal[o + 1] = (uint8_t)((t & 0xff) - 4);
             }
+            MAPF_RESET_TICK(6);  // stores
         }
         if (ok) break;
     }
@@ -301,6 +364,11 @@ __device__ __forceinline__ void reset_env_warp(const EnvDims &d, const int e, co
         }
     }
     if (lane == 0) steps[e] = 0;
+#ifdef MAPF_ENABLE_DIAG
+    MAPF_RESET_TICK(7);  // bitmap store
+    if (e == 0 && lane == 0)
+        for (int i = 0; i < 8; ++i) g_reset_cycles[i] = (unsigned long long)_acc[i];
+#endif
 }
 
 }  // namespace

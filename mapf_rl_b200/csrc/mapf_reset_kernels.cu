@@ -111,3 +111,11 @@ int mapf_launch_pregen(mapf_env *env, int min_count, cudaStream_t st)
     if (rc != MAPF_OK) return rc;
     return mapf_launch_pregen_bfs(env, min_count, st);
 }
+
+#ifdef MAPF_ENABLE_DIAG
+// diagnosis build only: cycles per generator phase of environment 0 in the last reset_kernel launch
+extern "C" int mapf_diag_reset_cycles(unsigned long long *out8)
+{
+    return cudaMemcpyFromSymbol(out8, g_reset_cycles, sizeof(unsigned long long) * 8) == cudaSuccess ? 0 : -1;
+}
+#endif

@@ -68,6 +68,8 @@ void mapf_set_rollout_tasks(int on) { rollout_tasks_ref() = on; }
 // diagnosis build only: per-item time stamps of the next rollout launches (profiles/tools/r2_rollout_timeline.py)
 static unsigned long long *g_trace = nullptr;
 static int g_trace_cap = 0;
+// cycles of the search phases of environment 0 inside rollout_kernel (each translation unit has its own copy of the counters:
+// this one reads the occ8 kernels' through mapf_diag_bfs_cycles_occ8)
 extern "C" int mapf_diag_rollout_trace(unsigned long long *d_buf, int capacity)
 {
     g_trace = d_buf, g_trace_cap = capacity;
