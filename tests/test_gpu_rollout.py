@@ -492,3 +492,47 @@ def test_rollout_bad_arguments():
     env.rollout(acts, chains=2)
     with pytest.raises(AssertionError):
         env.check()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("pregen", [2, 3, 0])
+def test_rollout_autoreset_graph_replay(rollout_tuning, pregen):
+    """A rollout with episode handling captured into a CUDA graph (due list, pre-generation kernels and the rollout kernel on the
+    capturing stream; the 'beside' form falls back to in-place re-generation while capturing) and replayed: every replay equals
+    an eager twin with the same episode settings."""
+    import torch
+    from mapf_rl_b200 import _native
+    B, N, L, T, cap = 192, 8, 12, 7, 5
+    rollout_tuning(1, 0, 0, 0)
+    _native.lib().mapf_debug_rollout_pregen(pregen)
+    try:
+        env, twin = make_env(B, N, L), make_env(B, N, L)
+        for e in (env, twin):
+            e.reset(seed=21, env_offset=0, density=0.2)
+            e.set_autoreset(cap, seed=21, env_offset=B, stride=B, density=0.2)
+        g = torch.Generator(device="cuda")
+        g.manual_seed(5)
+        acts = torch.randint(0, 5, (T, B, N), generator=g, device="cuda", dtype=torch.uint8)
+        rings = [torch.zeros(sh, dtype=dt, device="cuda") for sh, dt in
+                 (((T, B, N, 6, 9, 9), torch.uint8), ((T, B, N), torch.float32), ((T, B), torch.uint8), ((T, B), torch.int32))]
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):   # warm-up outside the capture (lazy allocations, module loading)
+            env.rollout(acts, out_obs=rings[0], out_rewards=rings[1], out_done=rings[2], out_steps=rings[3])
+        side.synchronize()
+        twin.rollout(acts)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            env.rollout(acts, out_obs=rings[0], out_rewards=rings[1], out_done=rings[2], out_steps=rings[3])
+        for it in range(4):
+            acts.copy_(torch.randint(0, 5, (T, B, N), generator=g, device="cuda", dtype=torch.uint8))
+            graph.replay()
+            o, r, d, s = twin.rollout(acts)
+            assert torch.equal(rings[0], o) and torch.equal(rings[1], r) and torch.equal(rings[2], d) and torch.equal(rings[3], s), it
+            assert torch.equal(env.agents_pos, twin.agents_pos) and torch.equal(env.goals_pos, twin.goals_pos)
+            assert torch.equal(env.navi_map, twin.navi_map)
+        assert int(env.episode_counts().sum()) > B      # episodes did end inside the replays
+        env.check()
+        twin.check()
+    finally:
+        _native.lib().mapf_debug_rollout_pregen(1)
