@@ -15,6 +15,9 @@ def test_signature_and_types():
     assert env.num_agents == config.num_agents and env.map_size == (config.map_length, config.map_length)
     assert env.map.shape == (20, 20) and env.agents_pos.shape == (6, 2) and env.goals_pos.dtype == np.int64
     assert env.steps == 0 and env.obs_radius == 4 and env.reward_fn == config.reward_fn
+    # a fresh instance: starts and goals are 12 distinct cells (environment.py:118-137 removes every drawn cell from its
+    # partition); checked BEFORE the step -- the instance is unseeded, and a step may put an agent on a goal
+    assert len({tuple(p) for p in env.agents_pos} | {tuple(g) for g in env.goals_pos}) == 12
     obs, pos = env.observe()
     assert obs.shape == (6, 6, 9, 9) and obs.dtype == np.bool_ and pos.dtype == np.int64
     (obs, pos), rewards, done, info = env.step([0, 1, 2, 3, 4, 0])
@@ -25,8 +28,6 @@ def test_signature_and_types():
         env.step([0, 1, 2, 3, 4, 5])
     with pytest.raises(AssertionError):
         env.step([0, 1])
-    # components: start and goal of every agent are connected => its own goal cell has navi bits around it
-    assert len({tuple(p) for p in env.agents_pos} | {tuple(g) for g in env.goals_pos}) == 12
 
 
 def test_adaptive_and_reset():
