@@ -145,6 +145,30 @@ __device__ __forceinline__ void env_step_gather(const StepParams &p, const int e
     // The cell -> agent grid of the step phase lives in the bit-stream buffer (the two are never live at
     // the same time).  It is never cleared: an entry is trusted only if it round-trips through s_cell.
     uint8_t *s_occ = reinterpret_cast<uint8_t *>(s_bits);
+    // RANKED (maps wider than 88 cells): L*L bytes of grid would be by far the largest buffer of the warp (14.4 KB at 120x120
+    // against 7.8 KB of bit stream for 128 agents), so "who stands on cell c" is answered from the agent BITMAP of the old
+    // positions instead: the occupant of a set bit is the agent whose cell has the same RANK among the set bits (row prefix
+    // of popcounts + popcount of the bits below inside the row), looked up in a rank -> agent table of N bytes that is
+    // rebuilt every step.  Claims of lower slots (K > 1) and the 'unique' check only need one bit per cell.
+    //   s_bits: [0, claim_words) claim bitmap (bit = cell index) | u8 s_pref[R] rank of a row's first bit | u8 s_r2a[N]
+    // Measured at 80x80 / 64 agents (RW = 3; profiles/r2_c4_ranked_lookup.jsonl): the ranked form lifts the whole-batch step
+    // kernel from 20 to 32 resident warps per SM and changes nothing (42.1 us against 41.0-41.7: the ~100 extra instructions
+    // per step cost what the occupancy gives; the rollout kernel loses 2 %), so the byte grid stays where it fits.
+    constexpr bool RANKED = MAPF_RANKED_LOOKUP(RW);
+    [[maybe_unused]] const int claim_words = ((L * L + 127) >> 7) << 2;
+    [[maybe_unused]] uint8_t *s_pref = reinterpret_cast<uint8_t *>(s_bits + claim_words);
+    [[maybe_unused]] uint8_t *s_r2a = s_pref + ((d.R + 3) & ~3);
+    [[maybe_unused]] auto rank_of = [&](const int X, const int Y) {  // padded coordinates; set bits below (X, Y)
+        const uint32_t *row = s_agent + X * RWS;
+        int rk = s_pref[X];
+        const int wq = Y >> 5;
+#pragma unroll
+        for (int w = 0; w < RW; ++w) {
+            const uint32_t m = w < wq ? 0xffffffffu : (w == wq ? ((1u << (Y & 31)) - 1u) : 0u);
+            rk += __popc(row[w] & m);
+        }
+        return rk;
+    };
     const bool navi_keep = p.flags & MAPF_STEPF_NAVI_KEEP;
     // the buffer that holds the slot's live heuristic maps (mapf_common.cuh)
     [[maybe_unused]] const uint32_t *navi_live = p.navi;
@@ -210,11 +234,47 @@ __device__ __forceinline__ void env_step_gather(const StepParams &p, const int e
                     act[k] = 0;
                 }
                 mycell[k] = px[k] * L + py[k];
-                s_cell[a] = valid[k] ? (uint16_t)mycell[k] : (uint16_t)0xffff;
-                if (valid[k]) s_occ[mycell[k]] = (uint8_t)a;
+                if constexpr (RANKED) {
+                    // bitmap of the OLD positions (s_agent is all zero between environments / steps)
+                    if (valid[k]) atomicOr(&s_agent[(px[k] + 4) * RWS + ((py[k] + 4) >> 5)], 1u << ((py[k] + 4) & 31));
+                } else {
+                    s_cell[a] = valid[k] ? (uint16_t)mycell[k] : (uint16_t)0xffff;
+                    if (valid[k]) s_occ[mycell[k]] = (uint8_t)a;
+                }
+            }
+            if constexpr (RANKED && K > 1) {  // claim bitmap: the last bit stream is still in there
+                for (int w = lane; w < (claim_words >> 2); w += 32) reinterpret_cast<uint4 *>(s_bits)[w] = make_uint4(0, 0, 0, 0);
             }
             asm volatile("cp.async.wait_all;" ::: "memory");
-            __syncwarp();  // staged obstacle bitmap, s_cell and s_occ visible to every lane
+            __syncwarp();  // staged obstacle bitmap, s_cell and s_occ (the old-position bitmap) visible to every lane
+            if constexpr (RANKED) {
+                // rank of every row's first bit: lane owns rows RW*lane .. RW*lane + RW - 1 (R <= 32 RW)
+                int cnt[RW], tot = 0;
+#pragma unroll
+                for (int i = 0; i < RW; ++i) {
+                    const int row = lane * RW + i;
+                    int c = 0;
+                    if (row < d.R) {
+#pragma unroll
+                        for (int w = 0; w < RW; ++w) c += __popc(s_agent[row * RWS + w]);
+                    }
+                    cnt[i] = c;
+                    tot += c;
+                }
+                int incl = tot;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int v = __shfl_up_sync(MAPF_FULL_MASK, incl, o);
+                    if (lane >= o) incl += v;
+                }
+                int run = incl - tot;
+#pragma unroll
+                for (int i = 0; i < RW; ++i) {
+                    const int row = lane * RW + i;
+                    if (row < d.R) s_pref[row] = (uint8_t)run;
+                    run += cnt[i];
+                }
+            }
 #pragma unroll
             for (int k = 0; k < K; ++k) {
                 // stay / move pass, environment.py:298-311
@@ -237,6 +297,12 @@ __device__ __forceinline__ void env_step_gather(const StepParams &p, const int e
                 s_tgt[k * 32 + lane] = mover[k] ? (uint16_t)tcell[k] : (uint16_t)0xffff;
             }
             __syncwarp();
+            if constexpr (RANKED) {
+#pragma unroll
+                for (int k = 0; k < K; ++k)
+                    if (valid[k]) s_r2a[rank_of(px[k] + 4, py[k] + 4)] = (uint8_t)(k * 32 + lane);
+                __syncwarp();
+            }
             // round 2: swap, environment.py:335-365 (order-independent form: both partners revert)
             bool swapped[K];
 #pragma unroll
@@ -245,20 +311,33 @@ __device__ __forceinline__ void env_step_gather(const StepParams &p, const int e
                 occ_ok[k] = false;
                 swapped[k] = false;
                 if (mover[k]) {
-                    const int j = s_occ[tcell[k]];
-                    occ_ok[k] = j < N && s_cell[j] == (uint16_t)tcell[k];
-                    occ_j[k] = j;
-                    swapped[k] = occ_ok[k] && s_tgt[j] == (uint16_t)mycell[k];
+                    if constexpr (RANKED) {
+                        const int X = tx[k] + 4, Y = ty[k] + 4;
+                        if ((s_agent[X * RWS + (Y >> 5)] >> (Y & 31)) & 1u) {
+                            occ_ok[k] = true;
+                            occ_j[k] = s_r2a[rank_of(X, Y)];
+                            swapped[k] = s_tgt[occ_j[k]] == (uint16_t)mycell[k];
+                        }
+                    } else {
+                        const int j = s_occ[tcell[k]];
+                        occ_ok[k] = j < N && s_cell[j] == (uint16_t)tcell[k];
+                        occ_j[k] = j;
+                        swapped[k] = occ_ok[k] && s_tgt[j] == (uint16_t)mycell[k];
+                    }
                 }
             }
             __syncwarp();
 #pragma unroll
-            for (int k = 0; k < K; ++k)
+            for (int k = 0; k < K; ++k) {
                 if (swapped[k]) {
                     s_tgt[k * 32 + lane] = 0xffff;
                     mover[k] = false;
                     code[k] = RC_COLLISION;
                 }
+                if constexpr (RANKED) {  // every lookup is done: take the old positions out of the bitmap again
+                    if (valid[k]) s_agent[(px[k] + 4) * RWS + ((py[k] + 4) >> 5)] = 0;
+                }
+            }
             __syncwarp();
             // round 3: vertex conflicts, environment.py:369-406, as the greatest fixed point:
             //   fail if the target's occupant is not a live mover,
@@ -269,8 +348,12 @@ __device__ __forceinline__ void env_step_gather(const StepParams &p, const int e
                 fail[k] = mover[k] && occ_ok[k] && s_tgt[occ_j[k]] == 0xffff;
                 bool lower_claim = false;
                 if (K > 1 && k > 0 && mover[k]) {
-                    const int c = s_occ[tcell[k]];  // claim left by a lower slot (verified, never cleared)
-                    lower_claim = c < N && (c >> 5) < k && s_tgt[c] == (uint16_t)tcell[k];
+                    if constexpr (RANKED) {
+                        lower_claim = (s_bits[tcell[k] >> 5] >> (tcell[k] & 31)) & 1u;  // only live movers of lower slots set bits
+                    } else {
+                        const int c = s_occ[tcell[k]];  // claim left by a lower slot (verified, never cleared)
+                        lower_claim = c < N && (c >> 5) < k && s_tgt[c] == (uint16_t)tcell[k];
+                    }
                 }
                 const unsigned mcode = mover[k] ? (unsigned)tcell[k] : (0x10000u | lane);
                 const unsigned m = __match_any_sync(MAPF_FULL_MASK, mcode);
@@ -278,7 +361,10 @@ __device__ __forceinline__ void env_step_gather(const StepParams &p, const int e
                 if (mover[k] && (!first || lower_claim)) fail[k] = true;
                 if (K > 1 && k + 1 < K) {
                     __syncwarp();
-                    if (mover[k]) s_occ[tcell[k]] = (uint8_t)(k * 32 + lane);
+                    if (mover[k]) {
+                        if constexpr (RANKED) atomicOr(&s_bits[tcell[k] >> 5], 1u << (tcell[k] & 31));
+                        else s_occ[tcell[k]] = (uint8_t)(k * 32 + lane);
+                    }
                     __syncwarp();
                 }
             }
@@ -322,14 +408,25 @@ __device__ __forceinline__ void env_step_gather(const StepParams &p, const int e
                 // environment.py:424-428: every agent must stand on a cell of its own (cannot fail after a correct step
                 // from a valid state; catches states injected through set_state / load)
                 __syncwarp();
-#pragma unroll
-                for (int k = 0; k < K; ++k)
-                    if (valid[k]) s_occ[px[k] * L + py[k]] = (uint8_t)(k * 32 + lane);
-                __syncwarp();
                 bool dup = false;
+                if constexpr (RANKED) {
+                    for (int w = lane; w < (claim_words >> 2); w += 32) reinterpret_cast<uint4 *>(s_bits)[w] = make_uint4(0, 0, 0, 0);
+                    __syncwarp();
 #pragma unroll
-                for (int k = 0; k < K; ++k)
-                    if (valid[k] && s_occ[px[k] * L + py[k]] != (uint8_t)(k * 32 + lane)) dup = true;
+                    for (int k = 0; k < K; ++k)
+                        if (valid[k]) {
+                            const int c = px[k] * L + py[k];
+                            if ((atomicOr(&s_bits[c >> 5], 1u << (c & 31)) >> (c & 31)) & 1u) dup = true;
+                        }
+                } else {
+#pragma unroll
+                    for (int k = 0; k < K; ++k)
+                        if (valid[k]) s_occ[px[k] * L + py[k]] = (uint8_t)(k * 32 + lane);
+                    __syncwarp();
+#pragma unroll
+                    for (int k = 0; k < K; ++k)
+                        if (valid[k] && s_occ[px[k] * L + py[k]] != (uint8_t)(k * 32 + lane)) dup = true;
+                }
                 if (__any_sync(MAPF_FULL_MASK, dup) && lane == 0) atomicOr(p.err, MAPF_ERRBIT_UNIQUE);
             }
 #pragma unroll

@@ -77,6 +77,9 @@ step_only_kernel(const StepParams p)
     const uint8_t *rows = p.actions + (size_t)blockIdx.x * 4 * N;
     const int nbytes = min(4, p.d.B - (int)blockIdx.x * 4) * N;
     const bool staged = ((reinterpret_cast<uintptr_t>(rows) | (uintptr_t)nbytes) & 15) == 0;
+    if constexpr (MAPF_RANKED_LOOKUP(RW)) {  // the ranked occupant lookup builds the old positions' bitmap in s_agent: it must start all-zero
+        for (int w = lane; w < p.obst_words; w += 32) s_agent[w] = 0;
+    }
     if (staged) {
         for (int w = threadIdx.x; w < (nbytes >> 4); w += blockDim.x)
             reinterpret_cast<uint4 *>(s_actions)[w] = __ldg(reinterpret_cast<const uint4 *>(rows) + w);
@@ -210,7 +213,9 @@ StepParams mapf_make_step_params(const mapf_env *env)
     // stream words: 15 head bits max + N*486 bits, +2 words of slack for the u16 tail read; the same
     // buffer holds the L*L-byte occupancy grid of the step phase
     const int stream_words = ((15 + d.N * MAPF_OBS_BYTES_PER_AGENT + 31) >> 5) + 2;
-    const int occ_words = (d.L * d.L + 3) >> 2;
+    // step-phase scratch in the same buffer: the L*L-byte occupancy grid, or (`RANKED` in mapf_step_device.cuh) the claim
+    // bitmap + row ranks + rank -> agent table
+    const int occ_words = MAPF_RANKED_LOOKUP(d.RW) ? ((((d.L * d.L + 127) >> 7) << 2) + ((d.R + 3) >> 2) + ((d.N + 3) >> 2)) : ((d.L * d.L + 3) >> 2);
     p.bits_words = stream_words > occ_words ? stream_words : occ_words;
     const int words = 2 * p.obst_words + p.bits_words + (32 * d.K) /* s_tgt + s_cell, u16 each */;
     p.warp_smem_words = (words + 3) & ~3;

@@ -79,6 +79,53 @@ def test_step_host_codes_vs_oracle(pinned):
     env.check()
 
 
+@pytest.mark.parametrize("L,N", [(80, 64), (72, 20), (120, 128)])
+def test_step_host_codes_large_maps_vs_oracle(L, N):
+    """The host-buffer step on maps wider than 56 cells (step-only kernel with the ranked occupant lookup + observe kernel
+    on the position snapshot), dense enough for swaps, vertex conflicts and chains; every step against the oracle."""
+    import torch
+    from mapf_rl_b200 import _native
+    lib = _native.lib()
+    rng = np.random.default_rng(L + N)
+    B = 9
+    insts = [random_instance(rng, L, N, 0.2) for _ in range(B)]
+    maps, agents, goals = (np.stack([i[j] for i in insts]) for j in range(3))
+    # crowd the agents of half the environments into one corner so that conflicts are frequent
+    for k in range(0, B, 2):
+        free = np.argwhere(maps[k][:12, :12] == 0)
+        if len(free) >= N:
+            agents[k] = free[rng.permutation(len(free))[:N]]
+    env = make_env(B, N, L)
+    env.load(maps, agents, goals)
+    ora = []
+    for k in range(B):
+        o = oracle.OracleEnv()
+        o.load(maps[k], agents[k], goals[k])
+        ora.append(o)
+    mk = lambda shape, dt: torch.zeros(shape, dtype=dt, pin_memory=True).numpy()
+    acts, codes = mk((B, N), torch.uint8), mk((B, N), torch.uint8)
+    done, steps = mk((B,), torch.uint8), mk((B,), torch.int32)
+    ring = torch.zeros((2, B, N, 6, 9, 9), dtype=torch.uint8, device="cuda:0")
+    vp = lambda a: a.ctypes.data_as(C.c_void_p)
+    table = env.reward_table
+    collisions = 0
+    for s in range(12):
+        acts[:] = rng.integers(0, 5, size=(B, N))
+        slot = ring[s % 2]
+        _native.check(lib.mapf_env_step_host_codes(env._h, vp(acts), vp(codes), vp(done), vp(steps), C.c_void_p(slot.data_ptr()),
+                                                   env._stream()))
+        c, d, st = codes.copy(), done.copy(), steps.copy()
+        obs = slot.cpu().numpy()
+        for k in range(B):
+            (oo, _), orw, od, _ = ora[k].step(acts[k])
+            assert np.array_equal(oo.astype(np.uint8), obs[k]), (s, k)
+            assert np.array_equal(np.asarray(orw, dtype=np.float32), table[c[k]]), (s, k)
+            assert int(od) == d[k] and st[k] == s + 1
+        collisions += int((c == 3).sum())
+    assert collisions > 0
+    env.check()
+
+
 def test_step_host_codes_full_size_back_to_back():
     """Many back-to-back calls at BASELINE configs[1] size over rotating page-locked action buffers: every call's host
     results are those of THAT step (a twin stepped on the device), although the call returns before its kernel ends."""
@@ -160,13 +207,15 @@ def test_load_validation():
     env.check()
 
 
-def test_device_unique_check():
+@pytest.mark.parametrize("L,N", [(10, 40), (72, 40), (100, 70)])
+def test_device_unique_check(L, N):
     """environment.py:424-428 on the device: with set_checks(check_unique=True) a step from a state with two agents on one
-    cell latches 'unique'; a correct step never does; the drop-in Environment enables it."""
+    cell latches 'unique'; a correct step never does; the drop-in Environment enables it.  Maps wider than 56 cells take
+    the ranked occupant lookup (one bit per cell instead of the byte grid)."""
     import torch
     from mapf_rl_b200 import _native
     rng = np.random.default_rng(2)
-    L, N, B = 10, 40, 7
+    B = 7
     insts = [random_instance(rng, L, N, 0.1) for _ in range(B)]
     maps, agents, goals = (np.stack([i[j] for i in insts]) for j in range(3))
     env = make_env(B, N, L)
