@@ -56,7 +56,13 @@ def raw_update(i, p):  # SumTree.update_device synchronises the stream after the
     _native.check(tree._lib.mapf_per_update(tree._h, C.c_void_p(i.data_ptr()), C.c_void_p(p.data_ptr()), int(i.numel()), tree._stream()))
 
 
-out = {"batch_sample_192_us": round(graph_time(lambda: tree.sample_device(192, u, beta=0.4)), 2),
+upd = dict(q_online=torch.randn(192, 5, device=dev), q_target_next=torch.randn(192, 5, device=dev),
+           action=torch.randint(0, 5, (192,), device=dev), reward=torch.randn(192, device=dev),
+           done=torch.zeros(192, device=dev), steps=torch.full((192,), 2.0, device=dev), idx=idx)
+cyc_out = tree.cycle(update=upd, sample_size=192, uniforms=u, beta=0.4)
+
+out = {"cycle_192_192_us": round(graph_time(lambda: tree.cycle(update=upd, sample_size=192, uniforms=u, beta=0.4, out=cyc_out)), 2),
+       "batch_sample_192_us": round(graph_time(lambda: tree.sample_device(192, u, beta=0.4)), 2),
        "batch_update_192_us": round(graph_time(lambda: raw_update(idx, newp)), 2),
        "episode_insert_256_us": round(graph_time(lambda: raw_update(ep_idx, ep_pr)), 2)}
 print(json.dumps(out))

@@ -63,6 +63,53 @@ def test_sumtree_vs_oracle_reference_capacity(cap, n):
             np.testing.assert_allclose(gw.cpu().numpy(), w, rtol=RTOL)
 
 
+@pytest.mark.parametrize("cap", [1 << 19, 1 << 12, 1 << 11, 1 << 10, 1 << 4, 2, 1])
+@pytest.mark.parametrize("n", [1, 37, 192, 256])
+def test_sumtree_sorted_batches_vs_oracle(cap, n):
+    """Non-decreasing leaf indices (what the stratified sampler returns, what an episode insert is) take the update path
+    that runs its level loop in shared memory (neighbour groups instead of L2 round trips): random sorted batches,
+    heavy duplicates (the last one wins), contiguous runs, one leaf n times, a batch at the tree's right edge; the tree
+    bit-equal to the oracle's after every round, and the sampler (top of the tree from shared memory) on top of it."""
+    from mapf_rl_b200 import SumTree
+    rng = np.random.default_rng(cap * 7 + n)
+    tree, ref = SumTree(cap), oracle.OracleSumTree(cap)
+    base = rng.random(min(cap, 4096)) + 0.01
+    for s in range(0, cap, 4096):   # a full tree to start from
+        ii = np.arange(s, min(cap, s + 4096), dtype=np.int64)
+        tree.batch_update(ii.copy(), base[: len(ii)])
+        ref.batch_update(ii.copy(), base[: len(ii)])
+    assert np.array_equal(tree.tree.cpu().numpy(), ref.tree)
+    for rd in range(6):
+        if rd == 0:
+            idx = np.sort(rng.integers(0, cap, size=n))
+        elif rd == 1:
+            idx = np.sort(rng.integers(0, max(1, min(cap, n // 3 + 1)), size=n) + rng.integers(0, max(1, cap - n)))
+        elif rd == 2:
+            idx = np.minimum(np.arange(n) + rng.integers(0, max(1, cap - n + 1)), cap - 1)
+        elif rd == 3:
+            idx = np.full(n, rng.integers(0, cap))
+        elif rd == 4:
+            idx = np.sort(np.maximum(cap - 1 - rng.integers(0, min(cap, 2 * n), size=n), 0))
+        else:
+            idx = np.sort(np.r_[rng.integers(0, cap, size=n - n // 2), np.repeat(rng.integers(0, cap), n // 2)])
+        idx = idx.astype(np.int64)
+        assert (np.diff(idx) >= 0).all() and idx.min() >= 0 and idx.max() < cap
+        pr = rng.random(n) ** 2 * 3
+        pr[rng.random(n) < 0.2] = 0.0
+        tree.batch_update(idx.copy(), pr)
+        ref.batch_update(idx.copy(), pr)
+        assert np.array_equal(tree.tree.cpu().numpy(), ref.tree), rd
+        tree.check()
+        if ref.tree[0] > 0:
+            B = 192
+            u = rng.random(B)
+            gi, gp, gw = tree.sample_device(B, u, beta=0.4)
+            ri, rp = ref.batch_sample(B, u)
+            assert np.array_equal(gi.cpu().numpy(), ri) and np.array_equal(gp.cpu().numpy(), rp)
+            if rp.min() > 0:
+                np.testing.assert_allclose(gw.cpu().numpy(), np.power(rp / rp.min(), -0.4), rtol=RTOL)
+
+
 def test_actor_td_golden_and_oracle():
     from mapf_rl_b200 import LocalBuffer
     from mapf_rl_b200.buffer import actor_td_errors
@@ -91,8 +138,9 @@ def test_actor_td_golden_and_oracle():
         assert np.array_equal(td[e], want), e
 
 
+@pytest.mark.parametrize("sorted_idx", [False, True])
 @pytest.mark.parametrize("double_q", [False, True])
-def test_learner_td_update(double_q):
+def test_learner_td_update(double_q, sorted_idx):
     import torch
     from mapf_rl_b200 import SumTree
     cap, slot = 1 << 12, 256
@@ -113,6 +161,8 @@ def test_learner_td_update(double_q):
         steps = rng.integers(1, 3, size=n).astype(np.float32)
         idx = rng.integers(0, cap, size=n).astype(np.int64)
         idx[:8] = idx[8:16]
+        if sorted_idx:   # the learner's indices come from the stratified sampler: sorted (stale ones masked in the middle)
+            idx = np.sort(idx)
         td, pr = tree.td_update(qo, qt, act, rew, done, steps, idx, old_ptr=old_ptr, ptr=ptr, slot_steps=slot,
                                 q_online_next=qn if double_q else None)
         if double_q:
