@@ -78,6 +78,12 @@ __device__ __forceinline__ uint2 ldg_policy(const uint2 *ptr, uint64_t pol)
     asm("ld.global.nc.L2::cache_hint.v2.b32 {%0, %1}, [%2], %3;" : "=r"(v.x), "=r"(v.y) : "l"(ptr), "l"(pol));
     return v;
 }
+__device__ __forceinline__ uint4 ldg_policy(const uint4 *ptr, uint64_t pol)
+{
+    uint4 v;
+    asm("ld.global.nc.L2::cache_hint.v4.b32 {%0, %1, %2, %3}, [%4], %5;" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(ptr), "l"(pol));
+    return v;
+}
 __device__ __forceinline__ void stg_policy(uint4 *ptr, const uint4 &v, uint64_t pol)
 {
     asm volatile("st.global.L2::cache_hint.v4.b32 [%0], {%1, %2, %3, %4}, %5;"
@@ -510,12 +516,29 @@ __device__ __forceinline__ void env_step_gather(const StepParams &p, const int e
                         for (int u = 0; u < 9; ++u) wr[u] = make_uint2(x + u, y);
                     } else
 #endif
-                    if (navi_keep) {
+                    {
+                        // the nine rows as FIVE aligned 16-byte loads (ten rows from the even row at or below the first):
+                        // every lane reads another line, so a warp-wide load costs 32 L1 wavefronts whatever its width --
+                        // 160 per agent slot instead of 288 with nine 8-byte loads (whole-batch step at C2 35.8 -> 35.0 us,
+                        // host-buffer step 5.7 -> 6.1 G agent-steps/s; profiles/r2_navi_row_loads.jsonl)
+                        const uint4 *nq = reinterpret_cast<const uint4 *>(nb - (x & 1));
+                        uint4 q[5];
+                        if (navi_keep) {
 #pragma unroll
-                        for (int u = 0; u < 9; ++u) wr[u] = ldg_policy(nb + u, pol_keep);
-                    } else {
+                            for (int u = 0; u < 5; ++u) q[u] = ldg_policy(nq + u, pol_keep);
+                        } else {
 #pragma unroll
-                        for (int u = 0; u < 9; ++u) wr[u] = __ldg(nb + u);
+                            for (int u = 0; u < 5; ++u) q[u] = __ldg(nq + u);
+                        }
+                        const bool odd = x & 1;
+#pragma unroll
+                        for (int u = 0; u < 9; ++u) {
+                            // row u of the window is loaded row u + odd; loaded row r = halves of q[r / 2]
+                            const uint2 ev = (u & 1) ? make_uint2(q[u / 2].z, q[u / 2].w) : make_uint2(q[u / 2].x, q[u / 2].y);
+                            const uint2 od = ((u + 1) & 1) ? make_uint2(q[(u + 1) / 2].z, q[(u + 1) / 2].w)
+                                                           : make_uint2(q[(u + 1) / 2].x, q[(u + 1) / 2].y);
+                            wr[u] = odd ? od : ev;
+                        }
                     }
                 }
                 auto mid = [&]() {
