@@ -79,7 +79,7 @@ def test_step_host_codes_vs_oracle(pinned):
     env.check()
 
 
-@pytest.mark.parametrize("L,N", [(80, 64), (72, 20), (120, 128)])
+@pytest.mark.parametrize("L,N", [(80, 64), (72, 20), (120, 128), (20, 7)])
 def test_step_host_codes_large_maps_vs_oracle(L, N):
     """The host-buffer step on maps wider than 56 cells (step-only kernel with the ranked occupant lookup + observe kernel
     on the position snapshot), dense enough for swaps, vertex conflicts and chains; every step against the oracle."""
