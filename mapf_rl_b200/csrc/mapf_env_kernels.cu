@@ -183,7 +183,11 @@ comm_mask_kernel(EnvDims d, const uint8_t *__restrict__ pos, int k_nearest, uint
     __syncwarp();
     for (int i = lane; i < N; i += 32) {
         const int xi = s_pos[warp][i] & 0xff, yi = s_pos[warp][i] >> 8;
-        uint32_t b0 = 0xffffffffu, b1 = 0xffffffffu, b2 = 0xffffffffu;  // three smallest keys, ascending
+        // three smallest keys, ascending.  Only agents inside the field of view can end up in the mask, and those lie within
+        // d^2 <= 2 r^2; an agent farther away can neither be one nor displace one from the three nearest: start at that bound
+        // (the insertion below then runs for the few close agents only)
+        constexpr uint32_t kFar = (uint32_t)(2 * MAPF_OBS_RADIUS * MAPF_OBS_RADIUS + 1) << 8;
+        uint32_t b0 = kFar, b1 = kFar, b2 = kFar;
         for (int j = 0; j < N; ++j) {
             const int dx = xi - (s_pos[warp][j] & 0xff), dy = yi - (s_pos[warp][j] >> 8);
             uint32_t key = ((uint32_t)(dx * dx + dy * dy) << 8) | (uint32_t)j;
@@ -197,7 +201,7 @@ comm_mask_kernel(EnvDims d, const uint8_t *__restrict__ pos, int k_nearest, uint
         const uint32_t best[3] = {b0, b1, b2};
 #pragma unroll
         for (int q = 0; q < 3; ++q) {
-            if (q < k_nearest && best[q] != 0xffffffffu) {
+            if (q < k_nearest && best[q] < kFar) {
                 const int j = best[q] & 0xff;
                 const int dx = abs(xi - (s_pos[warp][j] & 0xff)), dy = abs(yi - (s_pos[warp][j] >> 8));
                 if (dx <= MAPF_OBS_RADIUS && dy <= MAPF_OBS_RADIUS) {
@@ -212,9 +216,24 @@ comm_mask_kernel(EnvDims d, const uint8_t *__restrict__ pos, int k_nearest, uint
     }
     __syncwarp();
     uint8_t *o = out + (size_t)e * N * N;
-    for (int idx = lane; idx < N * N; idx += 32) {
-        const int i = idx / N, j = idx - i * N;
-        o[idx] = (s_bits[warp][i][j >> 5] >> (j & 31)) & 1u;
+    if ((N & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0) {
+        // 16 mask bytes (16 consecutive j of one row) per lane and store: bits -> bool bytes as in the observation path
+        const int per_row = N >> 4;
+        for (int c = lane; c < N * per_row; c += 32) {
+            const int i = c / per_row, j0 = (c - i * per_row) << 4;
+            const uint32_t b = (s_bits[warp][i][j0 >> 5] >> (j0 & 31)) & 0xffffu;
+            uint4 v;
+            v.x = ((b & 0xfu) * 0x00204081u) & 0x01010101u;
+            v.y = (((b >> 4) & 0xfu) * 0x00204081u) & 0x01010101u;
+            v.z = (((b >> 8) & 0xfu) * 0x00204081u) & 0x01010101u;
+            v.w = ((b >> 12) * 0x00204081u) & 0x01010101u;
+            reinterpret_cast<uint4 *>(o)[c] = v;
+        }
+    } else {
+        for (int idx = lane; idx < N * N; idx += 32) {
+            const int i = idx / N, j = idx - i * N;
+            o[idx] = (s_bits[warp][i][j >> 5] >> (j & 31)) & 1u;
+        }
     }
 }
 
