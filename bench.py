@@ -244,19 +244,26 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * el / args.steps, "higher_is_better": True, "scaling": args.scaling,
             "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": bench_config(args, None, None),
+            "config": bench_config(args),
+            "method": {"timing": "time.perf_counter around the K steps on the host", "episodes": "no episode handling (the port has no generator)",
+                       "instances": "host-side generator (mapf_rl_b200.instances), loaded into the port"},
             "cpu_baseline": cb,
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
 
-def bench_config(args, env, extra):
-    """`config` of the JSON line: identical keys for both arms (the driver compares them)."""
-    c = {"workload": workload_name(args), "num_envs": args.num_envs, "num_agents": args.num_agents, "map_length": args.map_length,
-         "obstacle_density": args.density, "actions": CONFIGS[args.config]["actions"], "config": args.config}
-    if extra:
-        c.update(extra)
-    return c
+def bench_config(args, env=None, extra=None):
+    """`config` of the JSON line: the workload, computed from the arguments alone, so that both arms (`--impl ours` and
+    `--impl reference`) print the SAME object (the driver compares them); what is specific to an arm -- how it is timed, where
+    its instances come from, its episode handling -- goes into the line's `method`."""
+    world = max(1, args.gpus)
+    per_gpu = args.num_envs // world if args.scaling == "strong" else args.num_envs
+    obs_mb = per_gpu * args.num_agents * 486 / 1e6
+    return {"workload": workload_name(args), "num_envs": args.num_envs, "num_agents": args.num_agents, "map_length": args.map_length,
+            "obstacle_density": args.density, "actions": CONFIGS[args.config]["actions"], "config": args.config,
+            "num_envs_per_gpu": per_gpu, "episode_cap": args.max_steps,
+            "l2": (f"no flush: every step writes {obs_mb:.0f} MB of observations per GPU into the next slot of a rotating ring; the ring "
+                   f"and the environments' state (heuristic maps) are several times the 126 MB L2")}
 
 
 # ---- GPU arm -------------------------------------------------------------------------------------------------------------------
@@ -467,16 +474,15 @@ def run_ours(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": args.warmup,
             "ms_per_step": ms / K, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
             "dtype": "u8", "data": "synthetic",
-            "config": bench_config(args, env, {
-                "num_envs_per_gpu": B,
+            "config": bench_config(args),
+            "method": {
+                "obs_ring_slots": R, "obs_ring_mb": round(R * B * N * 486 / 1e6), "state_arena_mb": round(env.arena_bytes / 1e6),
                 "instances": "device-side generator (mapf_env_reset), global env index = first_env + slot",
                 "episodes": (f"cap {cap} steps, reset on done / cap INSIDE the timed rollout (generator + BFS in the launch), step counters "
                              f"staggered over [0, {cap})" if cap > 0 else "no episode handling"),
-                "l2": f"no flush: per-step output {B * N * 486 / 1e6:.0f} MB rotates over a {R}-slot device ring "
-                      f"({R * B * N * 486 / 1e6:.0f} MB) + {env.arena_bytes / 1e6:.0f} MB state arena, both > 126 MB L2",
                 "extra_warmup": "0.3 s of untimed steps after W so SM clocks are under load",
                 "timing": f"CUDA events on the launching stream around ONE mapf_env_rollout call of K steps, enqueued behind a "
-                          f"{args.gate_cycles}-cycle device-side spin (host enqueue latency excluded); max over ranks"}),
+                          f"{args.gate_cycles}-cycle device-side spin (host enqueue latency excluded); max over ranks"},
             "clocks": clocks,
             "gpu_launches": K * chains if chains else 1,
             "per_rank_ms": {"min": min(ms_all), "median": med, "max": max(ms_all), "all": ms_all},

@@ -141,10 +141,10 @@ def run(args, METRIC, UNIT, ClockSampler, measured_hbm_peak, workload_name, benc
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8 (env) / bf16 (Q-net) / f64 (sum tree)",
             "data": "synthetic",
-            "config": bench_config(args, env, {"num_envs_per_gpu": B, "episode_cap": cap, "learner_every_actor_steps": args.learner_every,
-                                               "replay_slots": slots, "batch_size": config.batch_size,
-                                               "note": "Q-network GEMMs / convolutions stay in PyTorch (north star); the hand-written "
-                                                       "kernels are the env step, comm mask, replay gather, actor TD and the PER cycle"}),
+            "config": bench_config(args),
+            "method": {"learner_every_actor_steps": args.learner_every, "replay_slots": slots, "batch_size": config.batch_size,
+                       "note": "Q-network GEMMs / convolutions stay in PyTorch (north star); the hand-written "
+                               "kernels are the env step, comm mask, replay gather, actor TD and the PER cycle"},
             "clocks": clocks, "per_rank_ms": {"min": min(ms_all), "max": max(ms_all), "all": ms_all},
             "actor": {"episodes_published": actor.episodes - ep0, "transitions": actor.transitions - tr0, "resets": actor.resets},
             "learner": {"updates_in_timed_region": updates, "updates_total": learner.counter, "stats_last_update": stats,

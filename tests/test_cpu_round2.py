@@ -59,7 +59,14 @@ def test_bench_reference_arm_line():
     assert line["config"]["num_envs"] == 48 and line["config"]["num_agents"] == 32 and line["config"]["map_length"] == 40
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["value"] == line["value"]
-    assert set(line["config"]) >= {"workload", "num_envs", "num_agents", "map_length", "obstacle_density", "actions", "config"}
+    assert set(line["config"]) >= {"workload", "num_envs", "num_agents", "map_length", "obstacle_density", "actions", "config", "l2"}
+    # `config` is computed from the arguments alone: the GPU arm prints the same object (what differs between the arms is `method`)
+    import argparse
+    sys.path.insert(0, ROOT)
+    import bench
+    a = argparse.Namespace(config="c2", num_envs=48, num_agents=32, map_length=40, density=0.3, max_steps=256, scaling="weak", gpus=1)
+    assert bench.bench_config(a) == line["config"]
+    assert "timing" in line["method"]
 
 
 @pytest.mark.skipif(not ref_loader.available(), reason="reference tree not mounted")
