@@ -339,6 +339,7 @@ def test_rollout_full_size_c3_c4_vs_oracle(rollout_tuning, B, N, L, name):
     congestion-heavy stream): 48 sampled environments, every step, against the oracle (heuristic maps included), and the
     invariants of the rest (bool bytes, own centre clear, one agent per cell)."""
     import torch
+    torch.manual_seed(7)   # the action stream below draws from torch's default CUDA generator
     T = 10
     rollout_tuning(1, 0, 4 if name == "C4" else 0, 0)
     env = make_env(B, N, L)
