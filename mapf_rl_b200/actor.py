@@ -98,6 +98,10 @@ class BatchedActor:
         self.resets += 1
         # fresh instances: slot e of reset number r draws global stream (seed, r * B + e)
         self.env.reset(mask=None if first else mask, seed=self.seed, env_offset=self.resets * self.B, density=self.density)
+        # a generator that could not place its agents latches MAPF_ERRBIT_RESET and leaves the slot as it was: surface it
+        # here instead of stepping stale positions on a new map (one 4-byte status read per batch of episode ends; the
+        # Q-network forward between two steps is three orders of magnitude longer)
+        self.env.check()
         slots = self._take_slots(len(ids))
         self._slot_host[ids] = slots
         self.slot[idt] = torch.as_tensor(slots, device=self.dev)
