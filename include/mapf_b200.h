@@ -282,12 +282,14 @@ double *mapf_per_tree_ptr(mapf_per *tree);
 /* SumTree.batch_update (buffer.py:95-105): leaf[d_idx[k]] = d_prio[k] (duplicates: last in batch order
  * wins, numpy fancy assignment), then every touched ancestor = left + right, level by level.
  * d_idx is NOT modified (the reference mutates it in place, buffer.py:96; the Python mirror
- * reproduces that). */
+ * reproduces that).  Any order, any duplicates, any n; a batch of up to 256 non-decreasing indices -- what
+ * mapf_per_sample returns and what an episode insert (worker.py:87-94) is -- runs its level loop in shared memory
+ * (same bits, about half the time). */
 int mapf_per_update(mapf_per *tree, const int64_t *d_idx, const double *d_prio, int64_t n, void *stream);
 
 /* SumTree.batch_sample (buffer.py:56-78) with caller-supplied uniforms u in [0,1):
  * prefix_i = i*interval + u_i*interval.  d_weight_out (optional) = (p / min_batch p)^(-beta)
- * (worker.py:165-166). */
+ * (worker.py:165-166; fp32 powf, 1e-6 relative).  d_idx_out is non-decreasing (stratified prefixes). */
 int mapf_per_sample(mapf_per *tree, const double *d_uniforms, int64_t batch, int64_t *d_idx_out,
                     double *d_prio_out, float *d_weight_out, double beta, void *stream);
 
